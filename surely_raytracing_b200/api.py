@@ -1,0 +1,102 @@
+"""Thin Python face of librtb200.so (tests/bench plumbing; every call goes through the C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import RtbRenderParams, RtbSceneInfo, RtbStats
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """rtb_scene* wrapper: upload once, then render / trace / evaluate."""
+
+    def __init__(self, built, device: int = 0):
+        self._lib = capi.load_library()
+        self._h = C.c_void_p()
+        desc = built.desc if hasattr(built, "desc") else built
+        capi.check(self._lib, self._lib.rtb_scene_create(desc, device, C.byref(self._h)), "rtb_scene_create")
+        self._built = built  # keep the description's buffers alive
+        self.info = RtbSceneInfo()
+        capi.check(self._lib, self._lib.rtb_scene_info(self._h, C.byref(self.info)), "rtb_scene_info")
+
+    # --- the hot path -------------------------------------------------------------------------
+    def render(self, sample_begin: int = 0, sample_end: int | None = None, pipeline: int = 0,
+               collect_stats: bool = False, out: np.ndarray | None = None):
+        """rtb_render: returns (pixels[h,w,3] f64 sums, stats dict). `out` is accumulated into."""
+        h, w = self.info.image_height, self.info.image_width
+        if sample_end is None:
+            sample_end = self.info.spp_used
+        if out is None:
+            out = np.zeros((h, w, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.shape == (h, w, 3) and out.flags.c_contiguous
+        params = RtbRenderParams(sample_begin, sample_end, pipeline, 1 if collect_stats else 0)
+        stats = RtbStats()
+        capi.check(self._lib, self._lib.rtb_render(self._h, C.byref(params), _ptr(out), C.byref(stats)), "rtb_render")
+        return out, stats.as_dict()
+
+    def render_device(self, d_accum_ptr: int, sample_begin: int, sample_end: int, stream: int = 0,
+                      pipeline: int = 0, collect_stats: bool = False):
+        """rtb_render_device: accumulate into a caller-owned device float4 buffer, asynchronously."""
+        params = RtbRenderParams(sample_begin, sample_end, pipeline, 1 if collect_stats else 0)
+        capi.check(self._lib, self._lib.rtb_render_device(self._h, C.byref(params), C.c_void_p(d_accum_ptr),
+                                                          C.c_void_p(stream)), "rtb_render_device")
+
+    def render_stats(self) -> dict:
+        stats = RtbStats()
+        capi.check(self._lib, self._lib.rtb_render_stats(self._h, C.byref(stats)), "rtb_render_stats")
+        return stats.as_dict()
+
+    # --- parity harness -----------------------------------------------------------------------
+    def camera_rays(self) -> np.ndarray:
+        rays = np.zeros(self.info.image_height * self.info.image_width, dtype=capi.RAY_DTYPE)
+        capi.check(self._lib, self._lib.rtb_camera_rays(self._h, _ptr(rays)), "rtb_camera_rays")
+        return rays
+
+    def trace(self, rays: np.ndarray, flags: int = 0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=capi.HIT_DTYPE)
+        capi.check(self._lib, self._lib.rtb_trace(self._h, _ptr(rays), len(rays), flags, _ptr(hits)), "rtb_trace")
+        return hits
+
+    def medium_interval(self, medium: int, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        t0 = np.zeros(len(rays)); t1 = np.zeros(len(rays))
+        capi.check(self._lib, self._lib.rtb_medium_interval(self._h, medium, _ptr(rays), len(rays), _ptr(t0), _ptr(t1)),
+                   "rtb_medium_interval")
+        return t0, t1
+
+    def eval_texture(self, texture: int, uvp: np.ndarray) -> np.ndarray:
+        uvp = np.ascontiguousarray(uvp, dtype=np.float64).reshape(-1, 5)
+        out = np.zeros((len(uvp), 3))
+        capi.check(self._lib, self._lib.rtb_eval_texture(self._h, texture, _ptr(uvp), len(uvp), _ptr(out)), "rtb_eval_texture")
+        return out
+
+    def eval_light_pdf(self, origin_dir: np.ndarray) -> np.ndarray:
+        od = np.ascontiguousarray(origin_dir, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(od))
+        capi.check(self._lib, self._lib.rtb_eval_light_pdf(self._h, _ptr(od), len(od), _ptr(out)), "rtb_eval_light_pdf")
+        return out
+
+    def write_color(self, pixels: np.ndarray, spp: float, exposure: float = 0.0) -> np.ndarray:
+        px = np.ascontiguousarray(pixels, dtype=np.float64)
+        out = np.zeros(px.shape, dtype=np.uint8)
+        capi.check(self._lib, self._lib.rtb_write_color(self._h, _ptr(px), px.size // 3, float(spp), float(exposure), _ptr(out)),
+                   "rtb_write_color")
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.rtb_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
