@@ -1,0 +1,106 @@
+// device_scene.h -- the flat, device-resident form of a scene (host builder: flatten.cpp,
+// consumers: the kernels in kernels.cu).  Layout in HBM (all L2-resident: C4 is < 0.6 MB):
+//
+//   nodes      float4[4*n_nodes]   BVH2, one 64 B record per inner node holding BOTH children's
+//                                  boxes (fp32, padded outward so the fp32 slab test is conservative)
+//   prims      double2[6*n_prims]  96 B per primitive in BVH-leaf order, f64, world space (instance
+//                                  transforms baked in); surfaces first, then medium-boundary prims
+//   prim_info  int4[n_prims]       {kind, material, xform, canonical id}
+//   xforms     double2[n_xforms]   {cos, sin} of the composed rotate_y of an instance chain (uv only)
+//   media, materials, textures, texels (u8 RGB), perlin tables, lights: small tagged records.
+//
+// Precision split (DESIGN.md "Numerics"): BVH culling is fp32 and conservative; every
+// accept/reject decision that can change a result (primitive tests, medium intervals, light-pdf
+// probes) is f64 like the reference; shading arithmetic is fp32.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) || __has_include(<vector_types.h>)
+#include <vector_types.h>
+#else
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
+#endif
+
+namespace rtb {
+
+enum : int { PRIM_SPHERE = 0, PRIM_QUAD = 1 };
+enum : int { PRIM_FLAG_MOVING = 0x100 };
+enum : int { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
+enum : int { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_IMAGE = 2, TEX_NOISE = 3 };
+enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
+
+constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
+constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf (leaf ref = ~((first << 3) | (count - 1)))
+
+// primitive payload, 12 doubles (6 x double2):
+//   SPHERE: cx cy | cz r | cvx cvy | cvz - | - - | - -           (center(t) = c + t * cv)
+//   QUAD  : nx ny | nz d | Ax Ay | Az a0 | Bx By | Bz b0         (alpha = A.p + a0, beta = B.p + b0;
+//           n = unit normal, d = n.q, A = v x w, B = w x u, a0 = -A.q, b0 = -B.q, w = n/(n.n))
+constexpr int PRIM_D2 = 6;
+
+struct DMaterial {
+  int kind;
+  int texture;
+  int needs_uv;  // texture tree contains an IMAGE node: hit u,v must be computed
+  int pad;
+  float color[3];
+  float param;
+};
+
+struct DTexture {
+  int kind;
+  int a, b;       // CHECKER: even/odd texture; IMAGE: texel byte offset; NOISE: perlin table index
+  int width, height;
+  float color[3];
+  double scale;   // CHECKER: inv_scale; NOISE: scale
+};
+
+struct DMedium {
+  int first_prim, n_prims;  // boundary primitives (in `prims`, after the surfaces), DFS order
+  int material;
+  int pad;
+  double neg_inv_density;
+  float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
+};
+
+struct DLight {
+  int kind;
+  int pad;
+  double prim[12];  // same payload as `prims` (world space, time 0)
+  double q[3], u[3], v[3];  // QUAD: sampling frame
+  double area;
+};
+
+struct DCamera {
+  double center[3], pixel00[3], du[3], dv[3], disk_u[3], disk_v[3];
+  double recip_sqrt_spp;
+  int width, height, sqrt_spp, spp, max_depth, defocus;
+  float background[3];
+  float pad;
+};
+
+struct DScene {
+  const float4* nodes;
+  const double2* prims;
+  const int4* prim_info;
+  const double2* xforms;
+  const DMedium* media;
+  const DMaterial* materials;
+  const DTexture* textures;
+  const uint8_t* texels;
+  const float4* perlin_vec;   // 256 per table
+  const uint8_t* perlin_perm; // 768 per table: perm_x | perm_y | perm_z
+  const DLight* lights;
+  int n_nodes, n_surface_prims, n_prims, n_media, n_lights;
+  uint32_t flags;
+  uint32_t seed_lo, seed_hi;
+  DCamera cam;
+};
+
+struct DStats {
+  unsigned long long paths, segments, node_visits, prim_tests, medium_probes, nonfinite;
+};
+
+}  // namespace rtb

@@ -1,0 +1,454 @@
+// flatten.cpp -- see flatten.h
+#include "flatten.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <numeric>
+
+namespace rtb {
+namespace {
+
+const double kPi = 3.14159265358979323846;
+const double kInf = std::numeric_limits<double>::infinity();
+
+struct D3 { double x, y, z; };
+inline D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline D3 operator*(double s, D3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline D3 cross(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double length(D3 a) { return std::sqrt(dot(a, a)); }
+inline D3 unit(D3 a) { return (1. / length(a)) * a; }
+
+// composed instance transform: p_world = R_y(theta) * p_obj + t, with the matrix convention of
+// RotateY::hit's "object -> world" step (src/transform.rs:113-127): x' = c x + s z, z' = -s x + c z
+struct Xform {
+  double c = 1., s = 0.;
+  D3 t = {0., 0., 0.};
+  int id = 0;
+  D3 rot(D3 p) const { return {c * p.x + s * p.z, p.y, -s * p.x + c * p.z}; }
+  D3 point(D3 p) const { return rot(p) + t; }
+};
+
+struct Baked {
+  int kind, flags, material, xform, id;
+  double payload[12];
+  double lo[3], hi[3];
+};
+
+struct Builder {
+  const RtbSceneDesc& d;
+  HostScene& out;
+  std::string& err;
+  std::vector<char> seen;
+  std::vector<Baked> surfaces;
+  std::vector<std::vector<Baked>> boundaries;  // per medium
+  std::vector<int> medium_material;
+  std::vector<double> medium_density;
+  int next_id = 0;
+
+  Builder(const RtbSceneDesc& d_, HostScene& o, std::string& e) : d(d_), out(o), err(e), seen(d_.n_objects, 0) {}
+
+  bool fail(const std::string& m) { err = m; return false; }
+
+  void bake_quad(const RtbObject& o, const Xform& X, Baked& b) {  // Quad::new  src/object.rs:428-445
+    const D3 q = X.point({o.v[0], o.v[1], o.v[2]});
+    const D3 u = X.rot({o.v[3], o.v[4], o.v[5]});
+    const D3 v = X.rot({o.v[6], o.v[7], o.v[8]});
+    const D3 n = cross(u, v);
+    const D3 normal = unit(n);
+    const D3 w = (1. / dot(n, n)) * n;
+    const double dd = dot(normal, q);
+    const D3 A = cross(v, w), B = cross(w, u);  // alpha = w.(p x v) = p.(v x w); beta = w.(u x p) = p.(w x u)
+    const double p12[12] = {normal.x, normal.y, normal.z, dd, A.x, A.y, A.z, -dot(A, q), B.x, B.y, B.z, -dot(B, q)};
+    std::memcpy(b.payload, p12, sizeof(p12));
+    const D3 c[4] = {q, q + u, q + v, q + u + v};
+    for (int a = 0; a < 3; a++) { b.lo[a] = kInf; b.hi[a] = -kInf; }
+    for (const D3& p : c) {
+      const double pc[3] = {p.x, p.y, p.z};
+      for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], pc[a]); b.hi[a] = std::max(b.hi[a], pc[a]); }
+    }
+    b.kind = PRIM_QUAD;
+    b.flags = 0;
+  }
+
+  void bake_sphere(const RtbObject& o, const Xform& X, Baked& b) {  // Sphere::new / new_moving  src/object.rs:83-105
+    const D3 c = X.point({o.v[0], o.v[1], o.v[2]});
+    const D3 cv = X.rot({o.v[4], o.v[5], o.v[6]});
+    const bool moving = o.v[7] != 0.;
+    const double r = o.v[3];
+    const double p12[12] = {c.x, c.y, c.z, r, cv.x, cv.y, cv.z, 0., 0., 0., 0., 0.};
+    std::memcpy(b.payload, p12, sizeof(p12));
+    const double ar = std::fabs(r);
+    const double cc[3] = {c.x, c.y, c.z}, vv[3] = {cv.x, cv.y, cv.z};
+    for (int a = 0; a < 3; a++) {
+      b.lo[a] = cc[a] - ar; b.hi[a] = cc[a] + ar;
+      if (moving) { b.lo[a] = std::min(b.lo[a], cc[a] + vv[a] - ar); b.hi[a] = std::max(b.hi[a], cc[a] + vv[a] + ar); }
+    }
+    b.kind = PRIM_SPHERE;
+    b.flags = moving ? PRIM_FLAG_MOVING : 0;
+  }
+
+  int xform_id(const Xform& X) {
+    for (size_t i = 0; i < out.xforms.size(); i++)
+      if (out.xforms[i].x == X.c && out.xforms[i].y == X.s) return (int)i;
+    out.xforms.push_back(double2{X.c, X.s});
+    return (int)out.xforms.size() - 1;
+  }
+
+  // DFS in `add` order; `medium` >= 0 while inside a ConstantMedium boundary
+  bool walk(int oi, const Xform& X, int medium, int depth) {
+    if (oi < 0 || oi >= d.n_objects) return fail("object index out of range");
+    if (depth > 64) return fail("object graph deeper than 64 levels");
+    if (seen[oi]) return fail("object referenced twice: the graph must be a tree (flatten emits one node per occurrence)");
+    seen[oi] = 1;
+    const RtbObject& o = d.objects[oi];
+    switch (o.kind) {
+      case RTB_OBJ_SPHERE:
+      case RTB_OBJ_QUAD: {
+        if (o.material < 0 || o.material >= d.n_materials) return fail("material index out of range");
+        Baked b;
+        if (o.kind == RTB_OBJ_QUAD) bake_quad(o, X, b);
+        else bake_sphere(o, X, b);
+        b.material = o.material;
+        b.xform = xform_id(X);
+        b.id = next_id++;
+        for (int a = 0; a < 12; a++)
+          if (!std::isfinite(b.payload[a])) return fail("non-finite primitive (degenerate quad or bad coordinates)");
+        (medium >= 0 ? boundaries[medium] : surfaces).push_back(b);
+        return true;
+      }
+      case RTB_OBJ_LIST:
+      case RTB_OBJ_BVH: {
+        if (o.first < 0 || o.count < 0 || (long long)o.first + o.count > d.n_children) return fail("list child range out of bounds");
+        for (int k = 0; k < o.count; k++)
+          if (!walk(d.children[o.first + k], X, medium, depth + 1)) return false;
+        return true;
+      }
+      case RTB_OBJ_TRANSLATE: {  // src/transform.rs:57-69
+        Xform Y = X;
+        Y.t = X.t + X.rot({o.v[0], o.v[1], o.v[2]});
+        return walk(o.first, Y, medium, depth + 1);
+      }
+      case RTB_OBJ_ROTATE_Y: {  // src/transform.rs:143-146
+        const double radians = o.v[0] * (kPi / 180.);
+        const double sa = std::sin(radians), ca = std::cos(radians);
+        Xform Y = X;
+        Y.c = X.c * ca - X.s * sa;
+        Y.s = X.s * ca + X.c * sa;
+        return walk(o.first, Y, medium, depth + 1);
+      }
+      case RTB_OBJ_MEDIUM: {  // src/constant_medium.rs:23-29
+        if (medium >= 0) { err = "a ConstantMedium used as the boundary of another medium is not supported"; return false; }
+        if (o.material < 0 || o.material >= d.n_materials) return fail("medium material index out of range");
+        if (!(o.v[0] > 0.)) return fail("medium density must be positive");
+        boundaries.emplace_back();
+        medium_material.push_back(o.material);
+        medium_density.push_back(o.v[0]);
+        return walk(o.first, X, (int)boundaries.size() - 1, depth + 1);
+      }
+      default:
+        return fail("unknown object kind");
+    }
+  }
+};
+
+// ---- SAH BVH2 over surface primitives -------------------------------------------------------------
+struct Box {
+  double lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
+  void grow(const double* l, const double* h) {
+    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); }
+  }
+  double area() const {
+    const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+    if (x < 0. || y < 0. || z < 0.) return 0.;
+    return 2. * (x * y + y * z + z * x);
+  }
+};
+
+struct BuildNode {
+  Box box;
+  int left = -1, right = -1;   // children (BuildNode indices); -1 for a leaf
+  int first = 0, count = 0;    // leaf range in the ordered primitive index array
+};
+
+struct BvhBuilder {
+  const std::vector<Baked>& prims;
+  std::vector<int> order;
+  std::vector<BuildNode> nodes;
+  int max_depth = 0;
+  static constexpr double kTraversal = 1.0, kIntersect = 1.5;
+
+  explicit BvhBuilder(const std::vector<Baked>& p) : prims(p), order(p.size()) { std::iota(order.begin(), order.end(), 0); }
+
+  int build(int first, int count, int depth) {
+    max_depth = std::max(max_depth, depth);
+    BuildNode node;
+    for (int i = 0; i < count; i++) node.box.grow(prims[order[first + i]].lo, prims[order[first + i]].hi);
+    node.first = first;
+    node.count = count;
+    const int self = (int)nodes.size();
+    nodes.push_back(node);
+    if (count <= 1) return self;
+    // full-sweep SAH on the three axes (n is a few thousand: build time is irrelevant)
+    double best_cost = kInf;
+    int best_axis = -1, best_split = -1;
+    std::vector<int> idx(order.begin() + first, order.begin() + first + count);
+    std::vector<double> right_area(count);
+    for (int axis = 0; axis < 3; axis++) {
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return prims[a].lo[axis] + prims[a].hi[axis] < prims[b].lo[axis] + prims[b].hi[axis];
+      });
+      Box rb;
+      for (int i = count - 1; i > 0; i--) { rb.grow(prims[idx[i]].lo, prims[idx[i]].hi); right_area[i] = rb.area(); }
+      Box lb;
+      for (int i = 1; i < count; i++) {
+        lb.grow(prims[idx[i - 1]].lo, prims[idx[i - 1]].hi);
+        const double cost = lb.area() * i + right_area[i] * (count - i);
+        if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+      }
+    }
+    const double parent_area = std::max(node.box.area(), 1e-300);
+    const double split_cost = kTraversal + kIntersect * best_cost / parent_area;
+    const double leaf_cost = kIntersect * count;
+    if (count <= BVH_MAX_LEAF && leaf_cost <= split_cost) return self;
+    std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
+      return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
+    });
+    const int l = build(first, best_split, depth + 1);
+    const int r = build(first + best_split, count - best_split, depth + 1);
+    nodes[self].left = l;
+    nodes[self].right = r;
+    nodes[self].count = 0;
+    return self;
+  }
+};
+
+inline float round_down(double x) { float f = (float)x; return ((double)f > x) ? std::nextafterf(f, -INFINITY) : f; }
+inline float round_up(double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; }
+
+void emit_prim(HostScene& out, const Baked& b) {
+  out.prims.insert(out.prims.end(), b.payload, b.payload + 12);
+  out.prim_info.push_back(int4{b.kind | b.flags, b.material, b.xform, b.id});
+}
+
+bool texture_needs_uv(const RtbSceneDesc& d, int ti, int depth = 0) {
+  if (ti < 0 || ti >= d.n_textures || depth > 16) return false;
+  const RtbTexture& t = d.textures[ti];
+  if (t.kind == RTB_TEX_IMAGE) return true;
+  if (t.kind == RTB_TEX_CHECKER) return texture_needs_uv(d, t.a, depth + 1) || texture_needs_uv(d, t.b, depth + 1);
+  return false;
+}
+
+}  // namespace
+
+int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
+  if (d.abi_version != RTB_ABI_VERSION) { err = "abi version mismatch"; return RTB_ERR_INVALID; }
+  if (d.n_objects <= 0 || !d.objects) { err = "empty object array"; return RTB_ERR_INVALID; }
+  if (d.world < 0 || d.world >= d.n_objects ||
+      (d.objects[d.world].kind != RTB_OBJ_LIST && d.objects[d.world].kind != RTB_OBJ_BVH)) {
+    err = "world must be a list object";
+    return RTB_ERR_INVALID;
+  }
+  out = HostScene();
+  out.flags = d.flags;
+  out.seed = d.seed;
+  out.xforms.push_back(double2{1., 0.});  // id 0 = identity
+
+  // ---- textures / materials -----------------------------------------------------------------
+  for (int i = 0; i < d.n_textures; i++) {
+    const RtbTexture& t = d.textures[i];
+    DTexture o{};
+    o.kind = t.kind; o.a = t.a; o.b = t.b;
+    o.color[0] = (float)t.color[0]; o.color[1] = (float)t.color[1]; o.color[2] = (float)t.color[2];
+    o.scale = t.scale;
+    switch (t.kind) {
+      case RTB_TEX_SOLID: break;
+      case RTB_TEX_CHECKER:
+        if (t.a < 0 || t.a >= d.n_textures || t.b < 0 || t.b >= d.n_textures) { err = "checker child texture out of range"; return RTB_ERR_INVALID; }
+        break;
+      case RTB_TEX_IMAGE: {
+        if (t.a < 0 || t.a >= d.n_images) { err = "image index out of range"; return RTB_ERR_INVALID; }
+        const RtbImage& im = d.images[t.a];
+        if (im.width <= 0 || im.height < 0 || (im.height > 0 && !im.rgb)) { err = "bad image"; return RTB_ERR_INVALID; }
+        o.width = im.width; o.height = im.height;
+        o.a = (int)out.texels.size();
+        out.texels.insert(out.texels.end(), im.rgb, im.rgb + (size_t)3 * im.width * im.height);
+        break;
+      }
+      case RTB_TEX_NOISE:
+        if (t.a < 0 || t.a >= d.n_perlins) { err = "perlin index out of range"; return RTB_ERR_INVALID; }
+        break;
+      default: err = "unknown texture kind"; return RTB_ERR_INVALID;
+    }
+    out.textures.push_back(o);
+  }
+  for (int i = 0; i < d.n_perlins; i++) {
+    const RtbPerlin& p = d.perlins[i];
+    for (int k = 0; k < 256; k++) out.perlin_vec.push_back(float4{(float)p.ranvec[k][0], (float)p.ranvec[k][1], (float)p.ranvec[k][2], 0.f});
+    const int32_t* perms[3] = {p.perm_x, p.perm_y, p.perm_z};
+    for (int a = 0; a < 3; a++)
+      for (int k = 0; k < 256; k++) {
+        if (perms[a][k] < 0 || perms[a][k] > 255) { err = "perlin permutation entry out of range"; return RTB_ERR_INVALID; }
+        out.perlin_perm.push_back((uint8_t)perms[a][k]);
+      }
+  }
+  for (int i = 0; i < d.n_materials; i++) {
+    const RtbMaterial& m = d.materials[i];
+    DMaterial o{};
+    o.kind = m.kind; o.texture = m.texture;
+    o.color[0] = (float)m.color[0]; o.color[1] = (float)m.color[1]; o.color[2] = (float)m.color[2];
+    o.param = (float)m.param;
+    if (m.kind < RTB_MAT_LAMBERTIAN || m.kind > RTB_MAT_ISOTROPIC) { err = "unknown material kind"; return RTB_ERR_INVALID; }
+    const bool textured = m.kind == RTB_MAT_LAMBERTIAN || m.kind == RTB_MAT_DIFFUSE_LIGHT || m.kind == RTB_MAT_ISOTROPIC;
+    if (textured && (m.texture < 0 || m.texture >= d.n_textures)) { err = "material texture index out of range"; return RTB_ERR_INVALID; }
+    o.needs_uv = textured && texture_needs_uv(d, m.texture) ? 1 : 0;
+    out.materials.push_back(o);
+  }
+
+  // ---- object graph ---------------------------------------------------------------------------
+  Builder B(d, out, err);
+  if (!B.walk(d.world, Xform(), -1, 0)) return err.find("not supported") != std::string::npos ? RTB_ERR_UNSUPPORTED : RTB_ERR_INVALID;
+  if (B.surfaces.empty() && B.boundaries.empty()) { /* an empty world is legal: every ray misses */ }
+
+  // ---- lights: the `lights` list (src/main.rs:485-494); only Quad / Sphere sample, others are
+  //      the Hittable defaults pdf 0 / direction (1,0,0) (src/hittable.rs:46-52, object.rs:53-69)
+  for (int k = 0; k < d.n_lights; k++) {
+    const int li = d.lights[k];
+    if (li < 0 || li >= d.n_objects) { err = "light index out of range"; return RTB_ERR_INVALID; }
+    const RtbObject& o = d.objects[li];
+    DLight L{};
+    Baked b{};
+    if (o.kind == RTB_OBJ_QUAD) {
+      B.bake_quad(o, Xform(), b);
+      L.kind = LIGHT_QUAD;
+      const D3 u = {o.v[3], o.v[4], o.v[5]}, v = {o.v[6], o.v[7], o.v[8]};
+      L.area = length(cross(u, v));
+      for (int a = 0; a < 3; a++) { L.q[a] = o.v[a]; L.u[a] = o.v[3 + a]; L.v[a] = o.v[6 + a]; }
+    } else if (o.kind == RTB_OBJ_SPHERE) {
+      B.bake_sphere(o, Xform(), b);
+      L.kind = LIGHT_SPHERE;
+    } else if (o.kind == RTB_OBJ_LIST || o.kind == RTB_OBJ_BVH) {
+      err = "nested lists inside the light list are not supported";
+      return RTB_ERR_UNSUPPORTED;
+    } else {
+      L.kind = LIGHT_OTHER;
+    }
+    std::memcpy(L.prim, b.payload, sizeof(L.prim));
+    out.lights.push_back(L);
+  }
+
+  // ---- camera: Camera::new  src/render.rs:62-134 ------------------------------------------------
+  {
+    const RtbCamera& c = d.camera;
+    if (c.image_width <= 0 || c.samples_per_pixel <= 0 || c.max_depth < 0 || !(c.aspect_ratio > 0.)) { err = "bad camera"; return RTB_ERR_INVALID; }
+    int image_height = (int)((double)c.image_width / c.aspect_ratio);
+    if (image_height < 1) image_height = 1;
+    const D3 lookfrom = {c.lookfrom[0], c.lookfrom[1], c.lookfrom[2]}, lookat = {c.lookat[0], c.lookat[1], c.lookat[2]};
+    const D3 vup = {c.vup[0], c.vup[1], c.vup[2]};
+    const double theta = c.vfov * (kPi / 180.);
+    const double h = std::tan(theta / 2.);
+    const double focus_dist = c.focus_dist <= 0. ? 1. : c.focus_dist;  // Q2
+    const double viewport_height = 2. * h * focus_dist;
+    const double viewport_width = viewport_height * (double)c.image_width / (double)image_height;
+    const D3 w = unit(lookfrom - lookat), u = unit(cross(vup, w)), v = cross(w, u);
+    const D3 viewport_u = viewport_width * u, viewport_v = viewport_height * ((-1.) * v);
+    const D3 du = (1. / (double)c.image_width) * viewport_u, dv = (1. / (double)image_height) * viewport_v;
+    const D3 upper_left = lookfrom - (focus_dist * w) - ((1. / 2.) * viewport_u) - ((1. / 2.) * viewport_v);
+    const D3 pixel00 = upper_left + 0.5 * (du + dv);
+    const double defocus_radius = focus_dist * std::tan((c.defocus_angle / 2.) * (kPi / 180.));
+    const int root = (int)std::sqrt((double)c.samples_per_pixel);
+    const int spp = root * root;  // nearest_square (Q1)
+    const double sqrt_spp = std::sqrt((double)spp);
+    DCamera& C = out.cam;
+    std::memset(&C, 0, sizeof(C));
+    const D3 disk_u = defocus_radius * u, disk_v = defocus_radius * v;
+    const D3 vs[6] = {lookfrom, pixel00, du, dv, disk_u, disk_v};
+    double* dst[6] = {C.center, C.pixel00, C.du, C.dv, C.disk_u, C.disk_v};
+    for (int k = 0; k < 6; k++) { dst[k][0] = vs[k].x; dst[k][1] = vs[k].y; dst[k][2] = vs[k].z; }
+    C.recip_sqrt_spp = 1. / sqrt_spp;
+    C.width = c.image_width; C.height = image_height; C.sqrt_spp = (int)sqrt_spp; C.spp = spp;
+    C.max_depth = c.max_depth; C.defocus = c.defocus_angle <= 0. ? 0 : 1;
+    for (int a = 0; a < 3; a++) C.background[a] = (float)c.background[a];
+    if (spp < 1) { err = "samples_per_pixel rounds down to zero"; return RTB_ERR_INVALID; }
+    if ((long long)C.width * C.height > (1ll << 31) - 1) { err = "image too large"; return RTB_ERR_INVALID; }
+  }
+
+  // ---- BVH over the surfaces ----------------------------------------------------------------------
+  // fp32 slab padding: covers the rounding of the f64 origin to fp32 (<= 2^-24 |o|) for origins up to
+  // ~8x the scene magnitude M; the multiplicative slack in the kernel covers the slab arithmetic.
+  double M = 1.;
+  for (const Baked& b : B.surfaces)
+    for (int a = 0; a < 3; a++) M = std::max(M, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
+  for (const auto& bl : B.boundaries)
+    for (const Baked& b : bl)
+      for (int a = 0; a < 3; a++) M = std::max(M, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
+  for (int a = 0; a < 3; a++) M = std::max(M, std::fabs(out.cam.center[a]));
+  const double pad = M * 6e-7;
+
+  BvhBuilder bvh(B.surfaces);
+  std::vector<int> node_remap;
+  if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
+  if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
+  out.bvh_depth = bvh.max_depth;
+  for (int i : bvh.order) emit_prim(out, B.surfaces[i]);
+  out.n_surface_prims = (int)B.surfaces.size();
+
+  // inner nodes get consecutive device indices in DFS order (root = 0)
+  auto leaf_ref = [](int first, int count) { return ~((first << 3) | (count - 1)); };
+  std::function<int(int)> emit_node = [&](int bi) -> int {
+    const BuildNode& bn = bvh.nodes[bi];
+    if (bn.left < 0) return leaf_ref(bn.first, bn.count);
+    const int self = (int)out.nodes.size() / 4;
+    out.nodes.resize(out.nodes.size() + 4);
+    const int refs[2] = {emit_node(bn.left), emit_node(bn.right)};
+    const Box* cb[2] = {&bvh.nodes[bn.left].box, &bvh.nodes[bn.right].box};
+    float lo[2][3], hi[2][3];
+    for (int c = 0; c < 2; c++)
+      for (int a = 0; a < 3; a++) { lo[c][a] = round_down(cb[c]->lo[a] - pad); hi[c][a] = round_up(cb[c]->hi[a] + pad); }
+    float4* N = &out.nodes[4 * (size_t)self];
+    N[0] = float4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
+    N[1] = float4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
+    N[2] = float4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
+    float r0, r1;
+    std::memcpy(&r0, &refs[0], 4);
+    std::memcpy(&r1, &refs[1], 4);
+    N[3] = float4{r0, r1, 0.f, 0.f};
+    return self;
+  };
+  if (B.surfaces.empty()) {
+    // no surfaces: the kernels skip traversal when n_surface_prims == 0; keep one inert node
+    out.nodes = {float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}};
+  } else if (bvh.nodes[0].left < 0) {
+    // a single leaf: both children of the root reference it (the second test is a no-op by the
+    // tie rule -- the reference's BvhNode::new duplicates a lone object the same way, hittable.rs:161-162)
+    const Box& bx = bvh.nodes[0].box;
+    const float4 n0 = float4{round_down(bx.lo[0] - pad), round_up(bx.hi[0] + pad), round_down(bx.lo[1] - pad), round_up(bx.hi[1] + pad)};
+    const float lz = round_down(bx.lo[2] - pad), hz = round_up(bx.hi[2] + pad);
+    const int ref0 = leaf_ref(0, bvh.nodes[0].count);
+    float r0;
+    std::memcpy(&r0, &ref0, 4);
+    out.nodes = {n0, n0, float4{lz, hz, lz, hz}, float4{r0, r0, 0.f, 0.f}};
+  } else {
+    emit_node(0);
+  }
+
+  // ---- media: boundary primitives after the surfaces, in DFS order ----------------------------------
+  for (size_t mi = 0; mi < B.boundaries.size(); mi++) {
+    DMedium m{};
+    m.first_prim = (int)out.prim_info.size();
+    m.n_prims = (int)B.boundaries[mi].size();
+    m.material = B.medium_material[mi];
+    m.neg_inv_density = -1. / B.medium_density[mi];  // src/constant_medium.rs:26
+    Box bx;
+    for (const Baked& b : B.boundaries[mi]) { emit_prim(out, b); bx.grow(b.lo, b.hi); }
+    for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
+    out.media.push_back(m);
+  }
+  return RTB_OK;
+}
+
+}  // namespace rtb

@@ -1,0 +1,39 @@
+// flatten.h -- host-side scene compiler: RtbSceneDesc (object graph, f64) -> flat device arrays.
+//   * validates the description (indices, tree shape, depth);
+//   * assigns canonical primitive ids in DFS `add` order;
+//   * bakes Translate / RotateY chains into world-space primitives (src/transform.rs:57-135);
+//   * derives the camera frame exactly like Camera::new (src/render.rs:62-134);
+//   * builds one SAH BVH2 over all surface primitives (replaces BvhNode::new, src/hittable.rs:147-187,
+//     whose randomised median split is not reproduced -- closest hits do not depend on tree shape).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "device_scene.h"
+
+namespace rtb {
+
+struct HostScene {
+  std::vector<float4> nodes;        // 4 per inner node
+  std::vector<double> prims;        // 12 per primitive (BVH order; surfaces, then boundaries)
+  std::vector<int4> prim_info;
+  std::vector<double2> xforms;
+  std::vector<DMedium> media;
+  std::vector<DMaterial> materials;
+  std::vector<DTexture> textures;
+  std::vector<uint8_t> texels;
+  std::vector<float4> perlin_vec;
+  std::vector<uint8_t> perlin_perm;
+  std::vector<DLight> lights;
+  DCamera cam;
+  int n_surface_prims = 0;
+  int bvh_depth = 0;
+  uint32_t flags = 0;
+  uint64_t seed = 0;
+};
+
+// returns RTB_OK or a negative RTB_ERR_* with `err` set
+int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err);
+
+}  // namespace rtb

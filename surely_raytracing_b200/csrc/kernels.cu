@@ -1,0 +1,220 @@
+// kernels.cu -- sm_100a kernels of the hot path and their launch wrappers.
+//
+//   k_render_mega       persistent per-pixel integrator with per-lane path regeneration (A/B arm)
+//   k_wf_*              wavefront pipeline: ray-gen -> extend -> shade/accumulate over SoA queues
+//   k_trace & friends   deterministic parity harness (closest hit, medium intervals, KAT hooks)
+//   k_write_color       output stage (reference src/color.rs:8-33)
+//
+// No tensor cores anywhere: nothing on this path is a dense contraction.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "rtb_device.cuh"
+
+namespace rtb {
+
+// ------------------------------------------------------------------------------------------------
+// pixel <-> thread mapping: each warp owns an 8x4 pixel tile (coherent primary rays, similar
+// path lengths inside a warp).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tile_pixel(const DCamera& cam, long long warp_global, int lane, uint32_t& pixel) {
+  const int tiles_x = (cam.width + 7) >> 3;
+  const int tx = (int)(warp_global % tiles_x), ty = (int)(warp_global / tiles_x);
+  const int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+  pixel = (uint32_t)(y * cam.width + x);
+  return x < cam.width && y < cam.height;
+}
+
+__device__ __forceinline__ void flush_stats(const DStats& local, DStats* global) {
+  atomicAdd(&global->paths, local.paths);
+  atomicAdd(&global->segments, local.segments);
+  atomicAdd(&global->node_visits, local.node_visits);
+  atomicAdd(&global->prim_tests, local.prim_tests);
+  atomicAdd(&global->medium_probes, local.medium_probes);
+  atomicAdd(&global->nonfinite, local.nonfinite);
+}
+
+// ------------------------------------------------------------------------------------------------
+// megakernel: the loop of render_par_lights (reference src/render.rs:179-191) with one thread per
+// pixel.  A lane whose path ends immediately starts its next stratum, so every lane of the warp
+// keeps tracing segments until its pixel's sample range is exhausted (per-lane regeneration).
+// The pixel's sum is kept in f64 registers and added to the fp32 accumulation buffer once, by the
+// one thread that owns the pixel: no atomics, bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene S, long long s_begin,
+                                                     long long s_end, float4* __restrict__ accum,
+                                                     DStats* __restrict__ stats) {
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t pixel;
+  if (!tile_pixel(S.cam, warp_global, threadIdx.x & 31, pixel)) return;
+  DStats st = {0, 0, 0, 0, 0, 0};
+  double sum_r = 0., sum_g = 0., sum_b = 0.;
+  long long s = s_begin;
+  PathState ps;
+  bool alive = false;
+  float Lr = 0.f, Lg = 0.f, Lb = 0.f;
+  for (;;) {
+    if (!alive) {
+      if (s >= s_end) break;
+      generate_primary(S, pixel, (uint32_t)s, ps);
+      s++;
+      Lr = Lg = Lb = 0.f;
+      alive = true;
+      if (STATS) st.paths++;
+    }
+    Event ev;
+    if (STATS) st.segments++;
+    extend<STATS>(S, ps, ev, &st);
+    alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);
+    if (!alive) {
+      const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
+      if (finite || (S.flags & 2u)) {
+        sum_r += (double)Lr; sum_g += (double)Lg; sum_b += (double)Lb;
+      } else if (STATS) {
+        st.nonfinite++;
+      }
+    }
+  }
+  float4 a = accum[pixel];
+  a.x += (float)sum_r; a.y += (float)sum_g; a.z += (float)sum_b; a.w += (float)(s_end - s_begin);
+  accum[pixel] = a;
+  if (STATS) flush_stats(st, stats);
+}
+
+cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
+                               bool collect_stats, cudaStream_t stream, int* launches) {
+  const long long tiles = (long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
+  const int block = 128;
+  const long long blocks = (tiles * 32 + block - 1) / block;
+  if (collect_stats) k_render_mega<true><<<(unsigned)blocks, block, 0, stream>>>(S, s_begin, s_end, d_accum, d_stats);
+  else k_render_mega<false><<<(unsigned)blocks, block, 0, stream>>>(S, s_begin, s_end, d_accum, d_stats);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// wavefront pipeline -- implemented below (section "wavefront")
+// ------------------------------------------------------------------------------------------------
+size_t wavefront_workspace_bytes(const DScene&, int64_t) { return 0; }
+cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
+                                    bool collect_stats, void*, size_t, int64_t, cudaStream_t stream, int* launches) {
+  return launch_render_mega(S, s_begin, s_end, d_accum, d_stats, collect_stats, stream, launches);
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic parity harness
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S, const RtbRay* __restrict__ rays,
+                                               long long n, uint32_t flags, RtbHit* __restrict__ hits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RtbRay in = rays[i];
+  Ray r;
+  r.ox = in.origin[0]; r.oy = in.origin[1]; r.oz = in.origin[2];
+  r.dx = in.direction[0]; r.dy = in.direction[1]; r.dz = in.direction[2];
+  r.time = (float)in.time;
+  Hit best;
+  hit_reset(best);
+  if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, in.t_min, best);
+  else if (S.n_surface_prims > 0) closest_surface<false>(S, r, in.t_min, best, nullptr);
+  RtbHit out;
+  complete_hit(S, r, in.time, best, out);
+  hits[i] = out;
+}
+
+cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits, const int*,
+                         cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_trace<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, d_rays, n, flags, d_hits);
+  return cudaGetLastError();
+}
+
+__global__ void k_medium_interval(const __grid_constant__ DScene S, int medium, const RtbRay* __restrict__ rays,
+                                  long long n, double* __restrict__ t0, double* __restrict__ t1) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RtbRay in = rays[i];
+  Ray r;
+  r.ox = in.origin[0]; r.oy = in.origin[1]; r.oz = in.origin[2];
+  r.dx = in.direction[0]; r.dy = in.direction[1]; r.dz = in.direction[2];
+  r.time = (float)in.time;
+  double a, b;
+  if (medium_interval(S, S.media[medium], r, a, b)) { t0[i] = a; t1[i] = b; }
+  else { t0[i] = t1[i] = RTB_INF - RTB_INF; /* NaN */ }
+}
+cudaError_t launch_medium_interval(const DScene& S, int medium, const RtbRay* d_rays, int64_t n, double* d_t0,
+                                   double* d_t1, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_medium_interval<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, medium, d_rays, n, d_t0, d_t1);
+  return cudaGetLastError();
+}
+
+__global__ void k_eval_texture(const __grid_constant__ DScene S, int texture, const double* __restrict__ uvp,
+                               long long n, double* __restrict__ rgb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3 c = texture_value(S, texture, (float)uvp[5 * i], (float)uvp[5 * i + 1], uvp[5 * i + 2], uvp[5 * i + 3],
+                             uvp[5 * i + 4]);
+  rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+}
+cudaError_t launch_eval_texture(const DScene& S, int texture, const double* d_uvp, int64_t n, double* d_rgb,
+                                cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_eval_texture<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, texture, d_uvp, n, d_rgb);
+  return cudaGetLastError();
+}
+
+__global__ void k_eval_light_pdf(const __grid_constant__ DScene S, const double* __restrict__ od, long long n,
+                                 double* __restrict__ pdf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray probe;
+  probe.ox = od[6 * i]; probe.oy = od[6 * i + 1]; probe.oz = od[6 * i + 2];
+  probe.dx = od[6 * i + 3]; probe.dy = od[6 * i + 4]; probe.dz = od[6 * i + 5];
+  probe.time = 0.f;
+  double sum = 0.;
+  for (int k = 0; k < S.n_lights; k++) sum += light_pdf_one(S.lights[k], probe);
+  pdf[i] = sum * (1. / (double)S.n_lights);
+}
+cudaError_t launch_eval_light_pdf(const DScene& S, const double* d_od, int64_t n, double* d_pdf, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_eval_light_pdf<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, d_od, n, d_pdf);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// output stage: write_color  reference src/color.rs:8-33 (sRGB OETF :53-59, clamp [0,0.999],
+// `(256*x) as u8` saturating, NaN -> 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_write_color(const double* __restrict__ pixels, long long n, double scale, double exposure,
+                              uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = pixels[i] * scale;
+  if (exposure > 0.) x = 1. - pow(2.718281828459045, -exposure * x);
+  x = (x <= 0.0031308) ? 12.92 * x : 1.055 * pow(x, 1. / 2.4) - 0.055;
+  const double c = x < 0. ? 0. : (x > 0.999 ? 0.999 : x);
+  const double y = 256. * c;
+  out[i] = (y == y && y > 0.) ? (uint8_t)(y >= 255. ? 255 : (int)y) : 0;
+}
+cudaError_t launch_write_color(const double* d_pixels, int64_t n_values, double spp, double exposure, uint8_t* d_out,
+                               cudaStream_t stream) {
+  if (n_values <= 0) return cudaSuccess;
+  k_write_color<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(d_pixels, n_values, 1.0 / spp, exposure, d_out);
+  return cudaGetLastError();
+}
+
+__global__ void k_accum_to_f64(const float4* __restrict__ accum, long long n, double* __restrict__ rgb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = accum[i];
+  rgb[3 * i] = (double)a.x; rgb[3 * i + 1] = (double)a.y; rgb[3 * i + 2] = (double)a.z;
+}
+cudaError_t launch_accum_to_f64(const float4* d_accum, int64_t n_pixels, double* d_pixels_rgb, cudaStream_t stream) {
+  if (n_pixels <= 0) return cudaSuccess;
+  k_accum_to_f64<<<(unsigned)((n_pixels + 255) / 256), 256, 0, stream>>>(d_accum, n_pixels, d_pixels_rgb);
+  return cudaGetLastError();
+}
+
+}  // namespace rtb

@@ -1,0 +1,34 @@
+// kernels.h -- launch wrappers implemented in kernels.cu, called by api.cpp
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtb200.h"
+#include "device_scene.h"
+
+namespace rtb {
+
+struct WavefrontBuffers;  // owned by the scene (api.cpp allocates through wavefront_alloc)
+
+// one persistent launch: per-lane path regeneration over [s_begin, s_end) for every pixel
+cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
+                               bool collect_stats, cudaStream_t stream, int* launches);
+
+// wavefront pipeline: ray-gen / extend / shade+accumulate kernels over SoA ray queues
+size_t wavefront_workspace_bytes(const DScene& S, int64_t paths_per_wave);
+cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
+                                    bool collect_stats, void* d_workspace, size_t workspace_bytes,
+                                    int64_t paths_per_wave, cudaStream_t stream, int* launches);
+
+cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits,
+                         const int* d_material_of_prim_unused, cudaStream_t stream);
+cudaError_t launch_medium_interval(const DScene& S, int medium, const RtbRay* d_rays, int64_t n, double* d_t0,
+                                   double* d_t1, cudaStream_t stream);
+cudaError_t launch_eval_texture(const DScene& S, int texture, const double* d_uvp, int64_t n, double* d_rgb,
+                                cudaStream_t stream);
+cudaError_t launch_eval_light_pdf(const DScene& S, const double* d_od, int64_t n, double* d_pdf, cudaStream_t stream);
+cudaError_t launch_write_color(const double* d_pixels, int64_t n_values, double spp, double exposure, uint8_t* d_out,
+                               cudaStream_t stream);
+cudaError_t launch_accum_to_f64(const float4* d_accum, int64_t n_pixels, double* d_pixels_rgb, cudaStream_t stream);
+
+}  // namespace rtb

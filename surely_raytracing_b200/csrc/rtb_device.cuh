@@ -1,0 +1,661 @@
+// rtb_device.cuh -- device-side building blocks of the path-tracing hot path: Philox RNG,
+// f64 primitive tests, fp32 conservative BVH traversal, media, textures, pdfs, materials.
+//
+// Behavioural contract = reference src/render.rs:251-312 (ray_color) and everything it calls;
+// each function cites what it restates.  The arithmetic is this backend's own design:
+//   * instance transforms are baked, so there is one world-space BVH2 (no per-instance ray xform);
+//   * BVH slabs are fp32 over outward-padded boxes: a conservative cull only;
+//   * primitive tests / medium intervals / light-pdf probes are f64 with the reference's interval
+//     rules (quads closed, spheres open: Q4) -- B200 issues DFMA at half the FFMA rate, which makes
+//     "decide in f64" affordable and is what holds first-hit ids exact against the f64 reference;
+//   * shading (ONB, sampling maps, optics, textures) is fp32;
+//   * RNG is counter-based Philox4x32-10 keyed (pixel, sample, bounce) with fixed draw slots.
+//
+// The header also compiles as plain C++ (tests/emu) so the logic can be debugged without a GPU;
+// that build is a development aid and is never linked into librtb200.so.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rtb200.h"
+#include "device_scene.h"
+
+#if defined(__CUDACC__)
+#define RTB_DEV __device__ __forceinline__
+#define RTB_LDG(p) __ldg(p)
+#else
+#include <cmath>
+#include <cstring>
+#define RTB_DEV inline
+#define RTB_LDG(p) (*(p))
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline float __double2float_ru(double d) { float f = (float)d; return ((double)f < d) ? nextafterf(f, INFINITY) : f; }
+static inline float __double2float_rd(double d) { float f = (float)d; return ((double)f > d) ? nextafterf(f, -INFINITY) : f; }
+static inline void sincospif(float x, float* s, float* c) { *s = sinf(3.14159265358979323846f * x); *c = cosf(3.14159265358979323846f * x); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+#endif
+
+namespace rtb {
+
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr double PI_D = 3.14159265358979323846;
+constexpr double RTB_INF = __builtin_huge_val();  // +inf
+constexpr uint32_t PRIMARY_BOUNCE = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (pixel, sample, bounce, call), key = seed.
+// Replaces rand's ThreadRng behind src/utils.rs:5-15 (SURVEY Appendix A for the slot budget).
+// ------------------------------------------------------------------------------------------------
+struct Rand4 { float x, y, z, w; };
+
+RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+RTB_DEV float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // 24 bits in [0,1)
+RTB_DEV Rand4 rand4(const DScene& S, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t call) {
+  uint32_t o[4];
+  philox4x32_10(pixel, sample, bounce, call, S.seed_lo, S.seed_hi, o);
+  Rand4 r;
+  r.x = u01(o[0]); r.y = u01(o[1]); r.z = u01(o[2]); r.w = u01(o[3]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers (fp32 shading math)
+// ------------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+RTB_DEV V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RTB_DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RTB_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RTB_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+RTB_DEV V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+RTB_DEV float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RTB_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RTB_DEV V3 normalize(V3 a) { return rsqrtf(dot(a, a)) * a; }
+
+struct Ray {
+  double ox, oy, oz;  // origin: f64 (hit points must stay on their surface to ~1e-13, like the reference)
+  double dx, dy, dz;  // direction, not normalised (Q3); secondary directions are fp32-valued
+  float time;
+};
+
+// ------------------------------------------------------------------------------------------------
+// primitive tests, f64.  Upper bound CLOSED in both (the caller applies the reference's
+// tie rule); lower bound closed for quads (Interval::contains) and open for spheres
+// (Interval::surrounds) -- src/object.rs:161-163, 462, src/interval.rs:21-27 (Q4).
+// ------------------------------------------------------------------------------------------------
+// Quad::hit  src/object.rs:453-490, with alpha/beta through the precomputed A = v x w, B = w x u
+RTB_DEV bool quad_test(const double2* __restrict__ P, const Ray& r, double tmin, double tmax, double& t_out,
+                       double& a_out, double& b_out) {
+  const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
+  const double denom = n01.x * r.dx + n01.y * r.dy + n2d.x * r.dz;
+  if (fabs(denom) < 1e-8) return false;
+  const double t = (n2d.y - (n01.x * r.ox + n01.y * r.oy + n2d.x * r.oz)) / denom;
+  if (!(tmin <= t && t <= tmax)) return false;
+  const double px = r.ox + t * r.dx, py = r.oy + t * r.dy, pz = r.oz + t * r.dz;
+  const double2 A01 = RTB_LDG(P + 2), A2a = RTB_LDG(P + 3);
+  const double a = A01.x * px + A01.y * py + A2a.x * pz + A2a.y;
+  if ((a < 0.) || (1. < a)) return false;
+  const double2 B01 = RTB_LDG(P + 4), B2b = RTB_LDG(P + 5);
+  const double b = B01.x * px + B01.y * py + B2b.x * pz + B2b.y;
+  if ((b < 0.) || (1. < b)) return false;
+  t_out = t; a_out = a; b_out = b;
+  return true;
+}
+
+// Sphere::hit  src/object.rs:145-166 (root selection only; normal/uv are completed for the winner)
+RTB_DEV bool sphere_test(const double2* __restrict__ P, int moving, const Ray& r, double time, double tmin, double tmax,
+                         double& t_out) {
+  const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
+  double cx = c01.x, cy = c01.y, cz = c2r.x;
+  if (moving) {  // Sphere::center  src/object.rs:107-112
+    const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
+    cx += time * v01.x; cy += time * v01.y; cz += time * v2.x;
+  }
+  const double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
+  const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+  const double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
+  const double c = (ocx * ocx + ocy * ocy + ocz * ocz) - c2r.y * c2r.y;
+  const double disc = half_b * half_b - a * c;
+  if (disc < 0.) return false;
+  const double sqrtd = sqrt(disc);
+  double root = (-half_b - sqrtd) / a;
+  if (!(tmin < root && root <= tmax)) {
+    if (root > tmax) return false;  // the far root is even larger
+    root = (sqrtd - half_b) / a;
+    if (!(tmin < root && root <= tmax)) return false;
+  }
+  t_out = root;
+  return true;
+}
+
+// Tie rule equivalent to HittableList::hit's in-order scan (src/hittable.rs:92-106, Q7): a later
+// quad replaces an equal-t hit (closed interval), a later sphere does not (open interval).
+RTB_DEV bool tie_wins(int kind, int id, int best_kind, int best_id) {
+  if (kind == PRIM_QUAD) return best_kind != PRIM_QUAD || id > best_id;
+  return best_kind != PRIM_QUAD && id < best_id;
+}
+
+struct Hit {
+  double t;     // +inf: none
+  double a, b;  // quad planar coordinates of the winner
+  int prim;     // index into prims (BVH order); -1 none
+  int kind, id; // of the winner (tie rule)
+};
+
+RTB_DEV void hit_reset(Hit& h) { h.t = RTB_INF; h.a = 0.; h.b = 0.; h.prim = -1; h.kind = -1; h.id = -1; }
+
+RTB_DEV void test_prim(const DScene& S, int pi, const Ray& r, double tmin, Hit& best) {
+  const int4 info = RTB_LDG(S.prim_info + pi);
+  const double2* P = S.prims + (size_t)pi * PRIM_D2;
+  const int kind = info.x & 0xFF;
+  double t, a = 0., b = 0.;
+  bool hit;
+  if (kind == PRIM_QUAD) hit = quad_test(P, r, tmin, best.t, t, a, b);
+  else hit = sphere_test(P, info.x & PRIM_FLAG_MOVING, r, (double)r.time, tmin, best.t, t);
+  if (hit && (t < best.t || tie_wins(kind, info.w, best.kind, best.id))) {
+    best.t = t; best.a = a; best.b = b; best.prim = pi; best.kind = kind; best.id = info.w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest surface hit: fp32 BVH2 cull + f64 leaves.  Replaces HittableList::hit / BvhNode::hit /
+// Aabb::hit (src/hittable.rs:88-109, 216-236, src/object.rs:340-370) with the build's own tree.
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& best, DStats* st) {
+  const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
+  const float idx = 1.0f / (float)r.dx, idy = 1.0f / (float)r.dy, idz = 1.0f / (float)r.dz;
+  const float tmin32 = __double2float_rd(tmin);
+  float tbest32 = __double2float_ru(best.t);
+  int stack[BVH_STACK];
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    if (node >= 0) {
+      if (STATS) st->node_visits++;
+      const float4* N = S.nodes + 4 * (size_t)node;
+      const float4 n0 = RTB_LDG(N + 0), n1 = RTB_LDG(N + 1), n2 = RTB_LDG(N + 2), n3 = RTB_LDG(N + 3);
+      // fminf/fmaxf drop NaNs (0 * inf when the origin sits on a slab plane of a parallel ray)
+      float a0 = (n0.x - ox) * idx, a1 = (n0.y - ox) * idx;
+      float b0 = (n0.z - oy) * idy, b1 = (n0.w - oy) * idy;
+      float c0 = (n2.x - oz) * idz, c1 = (n2.y - oz) * idz;
+      const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+      const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+      a0 = (n1.x - ox) * idx; a1 = (n1.y - ox) * idx;
+      b0 = (n1.z - oy) * idy; b1 = (n1.w - oy) * idy;
+      c0 = (n2.z - oz) * idz; c1 = (n2.w - oz) * idz;
+      const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+      const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+      const bool h0 = tn0 <= fmaf(fabsf(tf0), 2e-6f, tf0);
+      const bool h1 = tn1 <= fmaf(fabsf(tf1), 2e-6f, tf1);
+      int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
+        stack[sp++] = ch1;
+        node = ch0;
+        continue;
+      }
+      if (h0) { node = ch0; continue; }
+      if (h1) { node = ch1; continue; }
+    } else {
+      const int leaf = ~node;
+      const int first = leaf >> 3, count = (leaf & 7) + 1;
+      for (int i = 0; i < count; i++) {
+        if (STATS) st->prim_tests++;
+        test_prim(S, first + i, r, tmin, best);
+      }
+      tbest32 = __double2float_ru(best.t);
+    }
+    if (sp == 0) break;
+    node = stack[--sp];
+  }
+}
+
+// linear scan over all surface primitives (RTB_TRACE_BRUTE_FORCE: validates the BVH cull)
+RTB_DEV void closest_surface_brute(const DScene& S, const Ray& r, double tmin, Hit& best) {
+  for (int i = 0; i < S.n_surface_prims; i++) test_prim(S, i, r, tmin, best);
+}
+
+// ------------------------------------------------------------------------------------------------
+// constant media.  ConstantMedium::hit  src/constant_medium.rs:41-95 (Q17), restated order-
+// independently: the boundary interval comes from two probes over the medium's own boundary
+// primitives; the free-flight event is accepted inside [max(t1,tmin), min(t2, t_closest)].
+// ------------------------------------------------------------------------------------------------
+RTB_DEV double boundary_probe(const DScene& S, const DMedium& m, const Ray& r, double tmin) {
+  Hit h;
+  hit_reset(h);
+  for (int i = 0; i < m.n_prims; i++) test_prim(S, m.first_prim + i, r, tmin, h);
+  return h.t;  // +inf: no hit
+}
+
+RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded box vs the whole line
+  const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
+  const float idx = 1.0f / (float)r.dx, idy = 1.0f / (float)r.dy, idz = 1.0f / (float)r.dz;
+  const float a0 = (m.lo[0] - ox) * idx, a1 = (m.hi[0] - ox) * idx;
+  const float b0 = (m.lo[1] - oy) * idy, b1 = (m.hi[1] - oy) * idy;
+  const float c0 = (m.lo[2] - oz) * idz, c1 = (m.hi[2] - oz) * idz;
+  const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
+  const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
+  return tn <= fmaf(fabsf(tf), 2e-6f, tf) + 1e-30f;
+}
+
+RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, double& t1, double& t2) {
+  if (!medium_line_cull(m, r)) return false;
+  t1 = boundary_probe(S, m, r, -RTB_INF);          // boundary.hit(r, UNIVERSE)        :46
+  if (!(t1 < RTB_INF)) return false;
+  t2 = boundary_probe(S, m, r, t1 + 0.0001);       // boundary.hit(r, (t1+1e-4, INF))  :49-55
+  return t2 < RTB_INF;
+}
+
+// returns the event parameter t (or +inf) for medium `mi`, given the closest surface so far
+RTB_DEV double medium_event(const DScene& S, int mi, const Ray& r, double tmin, double tmax, float U) {
+  const DMedium& m = S.media[mi];
+  double t1, t2;
+  if (!medium_interval(S, m, r, t1, t2)) return RTB_INF;
+  if (t1 < tmin) t1 = tmin;   // :58-60
+  if (t2 > tmax) t2 = tmax;   // :61-63
+  if (t1 >= t2) return RTB_INF;
+  if (t1 < 0.) t1 = 0.;       // :69-71
+  const double ray_length = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+  const double distance_inside_boundary = (t2 - t1) * ray_length;
+  const double hit_distance = m.neg_inv_density * (double)logf(U);  // U = 0 -> +inf: no event
+  if (hit_distance > distance_inside_boundary) return RTB_INF;
+  return t1 + hit_distance / ray_length;
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures  (src/texture.rs:18-131, src/perlin.rs:30-96, src/rt_image.rs:37-46)
+// ------------------------------------------------------------------------------------------------
+RTB_DEV float perlin_noise(const DScene& S, int table, double px, double py, double pz) {  // perlin.rs:30-54,74-96
+  const double fx = floor(px), fy = floor(py), fz = floor(pz);
+  const float u = (float)(px - fx), v = (float)(py - fy), w = (float)(pz - fz);
+  // `as i32` saturates; |p| stays far below 2^31 for every octave of the scenes in scope
+  const int i = (int)fmax(-2147483648.0, fmin(2147483647.0, fx));
+  const int j = (int)fmax(-2147483648.0, fmin(2147483647.0, fy));
+  const int k = (int)fmax(-2147483648.0, fmin(2147483647.0, fz));
+  const float uu = u * u * (3.f - 2.f * u), vv = v * v * (3.f - 2.f * v), ww = w * w * (3.f - 2.f * w);
+  const uint8_t* perm = S.perlin_perm + 768 * table;
+  const float4* vec = S.perlin_vec + 256 * table;
+  float accum = 0.f;
+#pragma unroll
+  for (int di = 0; di < 2; di++)
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+      for (int dk = 0; dk < 2; dk++) {
+        const int idx = RTB_LDG(perm + ((i + di) & 255)) ^ RTB_LDG(perm + 256 + ((j + dj) & 255)) ^
+                        RTB_LDG(perm + 512 + ((k + dk) & 255));
+        const float4 c = RTB_LDG(vec + idx);
+        const float wx = di ? uu : 1.f - uu, wy = dj ? vv : 1.f - vv, wz = dk ? ww : 1.f - ww;
+        accum += wx * wy * wz * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
+      }
+  return accum;
+}
+
+RTB_DEV float perlin_turb(const DScene& S, int table, double px, double py, double pz) {  // perlin.rs:56-72
+  float accum = 0.f, weight = 1.f;
+  for (int o = 0; o < 7; o++) {
+    accum += weight * perlin_noise(S, table, px, py, pz);
+    weight *= 0.5f;
+    px *= 2.; py *= 2.; pz *= 2.;
+  }
+  return fabsf(accum);
+}
+
+RTB_DEV V3 texture_value(const DScene& S, int ti, float u, float v, double px, double py, double pz) {
+  for (int guard = 0; guard < 16; guard++) {
+    const DTexture& t = S.textures[ti];
+    if (t.kind == TEX_SOLID) return v3(t.color[0], t.color[1], t.color[2]);  // texture.rs:44-46
+    if (t.kind == TEX_CHECKER) {  // texture.rs:71-81 (Q19): floor in f64, Rust `%` keeps the sign
+      const int x = (int)floor(t.scale * px), y = (int)floor(t.scale * py), z = (int)floor(t.scale * pz);
+      const int sum = (int)((unsigned)x + (unsigned)y + (unsigned)z);  // wrapping add, like a release build
+      ti = ((sum % 2) == 0) ? t.a : t.b;
+      continue;
+    }
+    if (t.kind == TEX_IMAGE) {  // texture.rs:95-107, rt_image.rs:37-46 (Q20)
+      if (t.height <= 0) return v3(0.f, 1.f, 1.f);
+      const float uc = __saturatef(u), vc = __saturatef(v);
+      unsigned i = (unsigned)(uc * (float)t.width), j = (unsigned)(vc * (float)t.height);
+      if (i > (unsigned)t.width - 1u) i = (unsigned)t.width - 1u;
+      unsigned y = (unsigned)t.height - j - 1u;  // wraps when j == height, then clamps
+      if (y > (unsigned)t.height - 1u) y = (unsigned)t.height - 1u;
+      const uint8_t* p = S.texels + t.a + 3 * ((size_t)y * t.width + i);
+      const float s = 1.0f / 255.0f;
+      return v3(RTB_LDG(p) * s, RTB_LDG(p + 1) * s, RTB_LDG(p + 2) * s);
+    }
+    // TEX_NOISE  texture.rs:127-130 (Q21)
+    const double sx = t.scale * px, sy = t.scale * py, sz = t.scale * pz;
+    const float g = 0.5f * (1.f + sinf((float)sz + 10.f * perlin_turb(S, t.a, sx, sy, sz)));
+    return v3(g, g, g);
+  }
+  return v3(0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling maps and pdfs (src/onb.rs, src/pdf.rs, src/vec3.rs:184-250) -- rejection loops are
+// replaced by direct maps with a fixed draw count (same distributions)
+// ------------------------------------------------------------------------------------------------
+struct Onb { V3 u, v, w; };
+RTB_DEV Onb onb_from_w(V3 w_in) {  // onb.rs:32-47
+  Onb o;
+  o.w = normalize(w_in);
+  const V3 a = fabsf(o.w.x) > 0.9f ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+  o.v = normalize(cross(o.w, a));
+  o.u = cross(o.w, o.v);
+  return o;
+}
+RTB_DEV V3 onb_local(const Onb& o, float a, float b, float c) { return a * o.u + (b * o.v + c * o.w); }  // onb.rs:24-30
+
+RTB_DEV V3 random_cosine_direction(float r1, float r2) {  // vec3.rs:240-250
+  float s, c;
+  sincospif(2.f * r1, &s, &c);
+  const float sr = sqrtf(r2);
+  return v3(c * sr, s * sr, sqrtf(1.f - r2));
+}
+RTB_DEV V3 random_unit_vector(float r1, float r2) {  // uniform sphere; vec3.rs:215-217 by direct map
+  const float z = 1.f - 2.f * r1;
+  const float rr = sqrtf(fmaxf(0.f, 1.f - z * z));
+  float s, c;
+  sincospif(2.f * r2, &s, &c);
+  return v3(rr * c, rr * s, z);
+}
+
+// get_sphere_uv  src/object.rs:114-120 (Q8) in f64 (parity harness and IMAGE textures)
+RTB_DEV void sphere_uv(double nx, double ny, double nz, double& u, double& v) {
+  const double theta = acos(-ny);
+  const double phi = atan2(-nz, nx) + PI_D;
+  const double inv_pi = 1.0 / PI_D;
+  u = phi * inv_pi * 0.5;
+  v = theta * inv_pi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// light list: HittableList::{pdf_value, random} over Quad/Sphere::{pdf_value, random}
+// (src/hittable.rs:115-129, src/object.rs:122-132, 190-212, 492-506; Q9-Q12)
+// ------------------------------------------------------------------------------------------------
+RTB_DEV double light_pdf_one(const DLight& L, const Ray& probe) {
+  const double2* P = reinterpret_cast<const double2*>(L.prim);
+  if (L.kind == LIGHT_QUAD) {  // Quad::pdf_value :492-501
+    double t, a, b;
+    if (!quad_test(P, probe, 0.001, RTB_INF, t, a, b)) return 0.;
+    const double len2 = probe.dx * probe.dx + probe.dy * probe.dy + probe.dz * probe.dz;
+    const double distance_squared = t * t * len2;
+    const double cosine = fabs((probe.dx * L.prim[0] + probe.dy * L.prim[1] + probe.dz * L.prim[2]) / sqrt(len2));
+    return distance_squared / (cosine * L.area);
+  }
+  if (L.kind == LIGHT_SPHERE) {  // Sphere::pdf_value :190-202 (time 0, motion ignored)
+    double t;
+    if (!sphere_test(P, 0, probe, 0., 0.001, RTB_INF, t)) return 0.;
+    const double ex = L.prim[0] - probe.ox, ey = L.prim[1] - probe.oy, ez = L.prim[2] - probe.oz;
+    const double cos_theta_max = sqrt(1. - L.prim[3] * L.prim[3] / (ex * ex + ey * ey + ez * ez));
+    return 1. / (2. * PI_D * (1. - cos_theta_max));
+  }
+  return 0.;  // Hittable default  src/hittable.rs:46-48
+}
+
+RTB_DEV float lights_pdf_value(const DScene& S, double ox, double oy, double oz, V3 dir) {
+  Ray probe;
+  probe.ox = ox; probe.oy = oy; probe.oz = oz;
+  probe.dx = (double)dir.x; probe.dy = (double)dir.y; probe.dz = (double)dir.z;
+  probe.time = 0.f;  // Ray::new  src/ray.rs:20-26
+  double sum = 0.;
+  for (int i = 0; i < S.n_lights; i++) sum += light_pdf_one(S.lights[i], probe);
+  return (float)(sum * (1. / (double)S.n_lights));
+}
+
+RTB_DEV V3 lights_random(const DScene& S, double ox, double oy, double oz, float upick, float r1, float r2) {
+  int pick = (int)(upick * (float)S.n_lights);  // random_int(0, n-1)  src/hittable.rs:127-128
+  if (pick > S.n_lights - 1) pick = S.n_lights - 1;
+  const DLight& L = S.lights[pick];
+  if (L.kind == LIGHT_QUAD) {  // Quad::random :503-506
+    const double a = (double)r1, b = (double)r2;
+    return v3((float)(L.q[0] + a * L.u[0] + b * L.v[0] - ox), (float)(L.q[1] + a * L.u[1] + b * L.v[1] - oy),
+              (float)(L.q[2] + a * L.u[2] + b * L.v[2] - oz));
+  }
+  if (L.kind == LIGHT_SPHERE) {  // Sphere::random :204-212, random_to_sphere :122-132
+    const double ex = L.prim[0] - ox, ey = L.prim[1] - oy, ez = L.prim[2] - oz;
+    const double dist2 = ex * ex + ey * ey + ez * ez;
+    const Onb uvw = onb_from_w(v3((float)ex, (float)ey, (float)ez));
+    const float z = 1.f + r2 * ((float)sqrt(1. - L.prim[3] * L.prim[3] / dist2) - 1.f);
+    float s, c;
+    sincospif(2.f * r1, &s, &c);
+    const float sq = sqrtf(1.f - z * z);
+    return onb_local(uvw, c * sq, s * sq, z);
+  }
+  return v3(1.f, 0.f, 0.f);  // Hittable default  src/hittable.rs:50-52
+}
+
+// full hit record of the winner, f64 (parity harness): Sphere::hit :168-183 / Quad::hit :477-489 and
+// the point/normal mapping of Translate/RotateY (already in world space here because instances are baked)
+RTB_DEV void complete_hit(const DScene& S, const Ray& r, double time64, const Hit& best, RtbHit& out) {
+  out.prim = -1; out.front_face = 0; out.material = -1; out.reserved = 0;
+  out.t = RTB_INF;
+  out.p[0] = out.p[1] = out.p[2] = 0.; out.normal[0] = out.normal[1] = out.normal[2] = 0.;
+  out.u = out.v = 0.;
+  if (best.prim < 0) return;
+  const int4 info = RTB_LDG(S.prim_info + best.prim);
+  const double2* P = S.prims + (size_t)best.prim * PRIM_D2;
+  const double t = best.t;
+  const double px = r.ox + t * r.dx, py = r.oy + t * r.dy, pz = r.oz + t * r.dz;
+  double nx, ny, nz, u, v;
+  if ((info.x & 0xFF) == PRIM_QUAD) {
+    nx = P[0].x; ny = P[0].y; nz = P[1].x;
+    u = best.a; v = best.b;
+  } else {
+    double cx = P[0].x, cy = P[0].y, cz = P[1].x;
+    if (info.x & PRIM_FLAG_MOVING) { cx += time64 * P[2].x; cy += time64 * P[2].y; cz += time64 * P[3].x; }
+    const double inv_r = 1. / P[1].y;
+    nx = (px - cx) * inv_r; ny = (py - cy) * inv_r; nz = (pz - cz) * inv_r;
+    const double2 cs = S.xforms[info.z];
+    sphere_uv(cs.x * nx - cs.y * nz, ny, cs.y * nx + cs.x * nz, u, v);
+  }
+  const bool front = (r.dx * nx + r.dy * ny + r.dz * nz) < 0.;
+  if (!front) { nx = -nx; ny = -ny; nz = -nz; }
+  out.prim = info.w; out.front_face = front ? 1 : 0; out.material = info.y;
+  out.t = t; out.p[0] = px; out.p[1] = py; out.p[2] = pz;
+  out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;
+  out.u = u; out.v = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one path segment: extend (closest event) + shade (emit / scatter / terminate)
+// ------------------------------------------------------------------------------------------------
+struct PathState {
+  Ray ray;
+  float bx, by, bz;  // throughput (product of attenuation * scattering_pdf / pdf)
+  uint32_t pixel, sample, bounce;
+};
+
+// get_ray  src/render.rs:218-249 (draw order: jitter x, jitter y, [disk], time)
+RTB_DEV void generate_primary(const DScene& S, uint32_t pixel, uint32_t sample, PathState& ps) {
+  const DCamera& cam = S.cam;
+  const int x = (int)(pixel % (uint32_t)cam.width), y = (int)(pixel / (uint32_t)cam.width);
+  const int s_j = (int)(sample / (uint32_t)cam.sqrt_spp), s_i = (int)(sample % (uint32_t)cam.sqrt_spp);
+  const Rand4 u = rand4(S, pixel, sample, PRIMARY_BOUNCE, 0);
+  const double px = (double)x + (-0.5 + cam.recip_sqrt_spp * ((double)s_i + (double)u.x));  // :246
+  const double py = (double)y + (-0.5 + cam.recip_sqrt_spp * ((double)s_j + (double)u.y));  // :247
+  const double sx = cam.pixel00[0] + px * cam.du[0] + py * cam.dv[0];
+  const double sy = cam.pixel00[1] + px * cam.du[1] + py * cam.dv[1];
+  const double sz = cam.pixel00[2] + px * cam.du[2] + py * cam.dv[2];
+  double ox = cam.center[0], oy = cam.center[1], oz = cam.center[2];
+  if (cam.defocus) {  // :226-230, 238-241; unit disk by the polar map instead of rejection
+    const Rand4 d = rand4(S, pixel, sample, PRIMARY_BOUNCE, 1);
+    const float rr = sqrtf(d.x);
+    float s, c;
+    sincospif(2.f * d.y, &s, &c);
+    const double dxk = (double)(rr * c), dyk = (double)(rr * s);
+    ox += dxk * cam.disk_u[0] + dyk * cam.disk_v[0];
+    oy += dxk * cam.disk_u[1] + dyk * cam.disk_v[1];
+    oz += dxk * cam.disk_u[2] + dyk * cam.disk_v[2];
+  }
+  ps.ray.ox = ox; ps.ray.oy = oy; ps.ray.oz = oz;
+  ps.ray.dx = sx - ox; ps.ray.dy = sy - oy; ps.ray.dz = sz - oz;
+  ps.ray.time = u.z;  // :233
+  ps.bx = ps.by = ps.bz = 1.f;
+  ps.pixel = pixel; ps.sample = sample; ps.bounce = 0;
+}
+
+struct Event {
+  double t;   // +inf: miss
+  double a, b;
+  int prim;   // >= 0 surface primitive (BVH order); -1 none
+  int medium; // >= 0: the event is a scatter inside this medium
+};
+
+// world.hit(r, Interval{0.0001, INF})  src/render.rs:264-270
+template <bool STATS>
+RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st) {
+  Hit best;
+  hit_reset(best);
+  if (S.n_surface_prims > 0) closest_surface<STATS>(S, ps.ray, 0.0001, best, st);
+  ev.t = best.t; ev.a = best.a; ev.b = best.b; ev.prim = best.prim; ev.medium = -1;
+  if (S.n_media > 0) {
+    Rand4 u;
+    for (int mi = 0; mi < S.n_media; mi++) {
+      if ((mi & 3) == 0) u = rand4(S, ps.pixel, ps.sample, ps.bounce, 1u + (uint32_t)(mi >> 2));
+      const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
+      if (STATS) st->medium_probes++;
+      const double tm = medium_event(S, mi, ps.ray, 0.0001, ev.t, U);
+      if (tm < ev.t) { ev.t = tm; ev.medium = mi; ev.prim = -1; }
+    }
+  }
+}
+
+// material response at the event; returns false when the path ends (contribution added to L)
+RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb, DStats* st,
+                   bool stats) {
+  const Ray& r = ps.ray;
+  if (!(ev.t < RTB_INF)) {  // miss: cam.background  src/render.rs:298-309
+    Lr += ps.bx * S.cam.background[0]; Lg += ps.by * S.cam.background[1]; Lb += ps.bz * S.cam.background[2];
+    return false;
+  }
+  const double px = r.ox + ev.t * r.dx, py = r.oy + ev.t * r.dy, pz = r.oz + ev.t * r.dz;  // Ray::at
+  V3 n;
+  bool front = true;
+  float tu = 0.f, tv = 0.f;
+  int mat_id;
+  if (ev.medium >= 0) {  // constant_medium.rs:82-90: arbitrary normal, front_face = true, u = v = 0
+    n = v3(1.f, 0.f, 0.f);
+    mat_id = S.media[ev.medium].material;
+  } else {
+    const int4 info = RTB_LDG(S.prim_info + ev.prim);
+    const double2* P = S.prims + (size_t)ev.prim * PRIM_D2;
+    mat_id = info.y;
+    const int needs_uv = S.materials[mat_id].needs_uv;
+    if ((info.x & 0xFF) == PRIM_QUAD) {
+      const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
+      front = (r.dx * n01.x + r.dy * n01.y + r.dz * n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
+      n = v3((float)n01.x, (float)n01.y, (float)n2d.x);
+      tu = (float)ev.a; tv = (float)ev.b;
+    } else {
+      const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
+      double cx = c01.x, cy = c01.y, cz = c2r.x;
+      if (info.x & PRIM_FLAG_MOVING) {
+        const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
+        cx += (double)r.time * v01.x; cy += (double)r.time * v01.y; cz += (double)r.time * v2.x;
+      }
+      const double inv_r = 1. / c2r.y;
+      const double nx = (px - cx) * inv_r, ny = (py - cy) * inv_r, nz = (pz - cz) * inv_r;  // object.rs:169
+      front = (r.dx * nx + r.dy * ny + r.dz * nz) < 0.;
+      n = v3((float)nx, (float)ny, (float)nz);
+      if (needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105)
+        const double2 cs = RTB_LDG(S.xforms + info.z);
+        double u64, v64;
+        sphere_uv(cs.x * nx - cs.y * nz, ny, cs.y * nx + cs.x * nz, u64, v64);
+        tu = (float)u64; tv = (float)v64;
+      }
+    }
+    if (!front) n = -n;
+  }
+  const DMaterial& m = S.materials[mat_id];
+  if (m.kind == MAT_DIFFUSE_LIGHT) {  // emitted: front face only; never scatters (Q16)  material.rs:210-221
+    if (front) {
+      const V3 e = texture_value(S, m.texture, tu, tv, px, py, pz);
+      Lr += ps.bx * e.x; Lg += ps.by * e.y; Lb += ps.bz * e.z;
+    }
+    return false;
+  }
+  const Rand4 u = rand4(S, ps.pixel, ps.sample, ps.bounce, 0);
+  V3 dir;
+  if (m.kind == MAT_METAL) {  // material.rs:125-134 (Q14): always scatters
+    const V3 ud = normalize(v3((float)r.dx, (float)r.dy, (float)r.dz));
+    const V3 refl = ud - (2.f * dot(ud, n)) * n;
+    dir = normalize(refl) + m.param * random_unit_vector(u.z, u.w);
+    ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
+  } else if (m.kind == MAT_DIELECTRIC) {  // material.rs:167-191 (Q15), vec3.rs:219-229
+    const float ratio = front ? 1.0f / m.param : m.param;
+    const V3 ud = normalize(v3((float)r.dx, (float)r.dy, (float)r.dz));
+    const float cos_theta = fminf(dot(-ud, n), 1.f);
+    const float sin_theta = sqrtf(1.f - cos_theta * cos_theta);
+    bool reflect_it = ratio * sin_theta > 1.f;
+    if (!reflect_it) {
+      float r0 = (1.f - ratio) / (1.f + ratio);
+      r0 = r0 * r0;
+      const float x = 1.f - cos_theta, x2 = x * x;
+      reflect_it = (r0 + (1.f - r0) * (x2 * x2 * x)) > u.x;
+    }
+    if (reflect_it) {
+      dir = ud - (2.f * dot(ud, n)) * n;
+    } else {
+      const V3 perp = ratio * (ud + cos_theta * n);
+      const V3 par = -sqrtf(fabsf(1.f - dot(perp, perp))) * n;
+      dir = perp + par;
+    }
+    ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
+  } else {
+    // PdfPtr arm  src/render.rs:278-293: MixturePDF(HittablePDF(lights), material pdf)  pdf.rs:102-127
+    const V3 atten = texture_value(S, m.texture, tu, tv, px, py, pz);
+    const bool lambert = m.kind == MAT_LAMBERTIAN;
+    Onb uvw;
+    if (lambert) uvw = onb_from_w(n);  // CosinePDF::new  pdf.rs:60-66
+    const bool have_lights = S.n_lights > 0;  // empty list: material pdf alone (F2)
+    if (have_lights && u.x < 0.5f) {
+      dir = lights_random(S, px, py, pz, u.y, u.z, u.w);
+    } else if (lambert) {
+      const V3 c = random_cosine_direction(u.z, u.w);
+      dir = onb_local(uvw, c.x, c.y, c.z);
+    } else {
+      dir = random_unit_vector(u.z, u.w);  // SpherePDF::generate  pdf.rs:51-53
+    }
+    const V3 udir = normalize(dir);
+    float mat_pdf, scattering_pdf;
+    if (lambert) {
+      mat_pdf = fmaxf(0.f, dot(udir, uvw.w) * (1.0f / PI_F));              // CosinePDF::value  pdf.rs:69-73
+      const float cos_theta = dot(n, udir);                                 // Lambertian::scattering_pdf :100-109
+      scattering_pdf = cos_theta < 0.f ? 0.f : cos_theta * (1.0f / PI_F);
+    } else {
+      mat_pdf = 1.0f / (4.0f * PI_F);                                       // SpherePDF::value  pdf.rs:47-49
+      scattering_pdf = (S.flags & 1u) ? 0.f : 1.0f / (4.0f * PI_F);         // F3 (RTB_FLAG_ISO_PDF_ZERO)
+    }
+    float pdf_val = mat_pdf;
+    if (have_lights) pdf_val = 0.5f * lights_pdf_value(S, px, py, pz, dir) + 0.5f * mat_pdf;  // pdf.rs:116-118
+    if (!(S.flags & 2u)) {  // default NaN policy (Q22): zero / non-finite pdf -> the sample contributes nothing
+      if (!(pdf_val > 0.f) || !(pdf_val < 3.0e38f)) {
+        if (stats) st->nonfinite++;
+        return false;
+      }
+    }
+    const float wgt = scattering_pdf / pdf_val;
+    ps.bx *= atten.x * wgt; ps.by *= atten.y * wgt; ps.bz *= atten.z * wgt;
+    if (!(S.flags & 2u) && ps.bx == 0.f && ps.by == 0.f && ps.bz == 0.f) return false;  // dead path: result is 0
+  }
+  ps.ray.ox = px; ps.ray.oy = py; ps.ray.oz = pz;  // Ray::new_timed(rec.p, dir, r.time())
+  ps.ray.dx = (double)dir.x; ps.ray.dy = (double)dir.y; ps.ray.dz = (double)dir.z;
+  ps.bounce++;
+  return ps.bounce < (uint32_t)S.cam.max_depth;  // depth <= 0 -> (0,0,0)  src/render.rs:260-262
+}
+
+}  // namespace rtb

@@ -1,0 +1,142 @@
+// tests/emu/emu.cpp -- DEVELOPMENT AID, NOT PRODUCT and NOT a fallback.
+// Compiles the device header (csrc/rtb_device.cuh) and the host flattener as plain C++ so that the
+// kernel logic can be exercised in a container without a GPU (tests/test_emu_*.py compare it with
+// the oracle).  librtb200.so never links or calls this; it exists only to catch logic bugs before
+// GPU time is spent.  Moving-sphere time is fp32 here exactly as in the render kernels.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../surely_raytracing_b200/csrc/flatten.h"
+#include "../../surely_raytracing_b200/csrc/rtb_device.cuh"
+
+using namespace rtb;
+
+namespace {
+struct Emu {
+  HostScene host;
+  DScene dev{};
+  std::vector<double2> prims2;
+};
+thread_local std::string g_err;
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+void* emu_scene_create(const RtbSceneDesc* d) {
+  Emu* e = new Emu();
+  std::string err;
+  if (flatten_scene(*d, e->host, err) != RTB_OK) { g_err = err; delete e; return nullptr; }
+  const HostScene& h = e->host;
+  e->prims2.resize(h.prims.size() / 2);
+  std::memcpy(e->prims2.data(), h.prims.data(), h.prims.size() * sizeof(double));
+  DScene& D = e->dev;
+  D.nodes = h.nodes.data(); D.prims = e->prims2.data(); D.prim_info = h.prim_info.data(); D.xforms = h.xforms.data();
+  D.media = h.media.data(); D.materials = h.materials.data(); D.textures = h.textures.data(); D.texels = h.texels.data();
+  D.perlin_vec = h.perlin_vec.data(); D.perlin_perm = h.perlin_perm.data(); D.lights = h.lights.data();
+  D.n_nodes = (int)h.nodes.size() / 4; D.n_surface_prims = h.n_surface_prims; D.n_prims = (int)h.prim_info.size();
+  D.n_media = (int)h.media.size(); D.n_lights = (int)h.lights.size();
+  D.flags = h.flags; D.seed_lo = (uint32_t)h.seed; D.seed_hi = (uint32_t)(h.seed >> 32);
+  D.cam = h.cam;
+  return e;
+}
+void emu_scene_destroy(void* p) { delete static_cast<Emu*>(p); }
+
+int emu_scene_info(void* p, RtbSceneInfo* info) {
+  const Emu* e = static_cast<Emu*>(p);
+  std::memset(info, 0, sizeof(*info));
+  info->image_width = e->host.cam.width; info->image_height = e->host.cam.height;
+  info->spp_used = e->host.cam.spp; info->sqrt_spp = e->host.cam.sqrt_spp; info->max_depth = e->host.cam.max_depth;
+  info->n_surface_prims = e->host.n_surface_prims;
+  info->n_boundary_prims = (int)e->host.prim_info.size() - e->host.n_surface_prims;
+  info->n_media = (int)e->host.media.size(); info->n_bvh_nodes = (int)e->host.nodes.size() / 4;
+  info->n_lights = (int)e->host.lights.size(); info->bvh_depth = e->host.bvh_depth; info->device = -1;
+  return 0;
+}
+
+// the body of k_render_mega for every pixel, sequentially
+int emu_render(void* p, long long s_begin, long long s_end, double* rgb, unsigned long long* stats6) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  DStats st = {0, 0, 0, 0, 0, 0};
+  const int n = S.cam.width * S.cam.height;
+  for (int pixel = 0; pixel < n; pixel++) {
+    double sr = 0, sg = 0, sb = 0;
+    for (long long s = s_begin; s < s_end; s++) {
+      PathState ps;
+      generate_primary(S, (uint32_t)pixel, (uint32_t)s, ps);
+      st.paths++;
+      float Lr = 0, Lg = 0, Lb = 0;
+      bool alive = true;
+      while (alive) {
+        Event ev;
+        st.segments++;
+        extend<true>(S, ps, ev, &st);
+        alive = shade(S, ps, ev, Lr, Lg, Lb, &st, true);
+      }
+      const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
+      if (finite || (S.flags & 2u)) { sr += Lr; sg += Lg; sb += Lb; } else st.nonfinite++;
+    }
+    rgb[3 * pixel] += (double)(float)sr; rgb[3 * pixel + 1] += (double)(float)sg; rgb[3 * pixel + 2] += (double)(float)sb;
+  }
+  if (stats6) { stats6[0] = st.paths; stats6[1] = st.segments; stats6[2] = st.node_visits; stats6[3] = st.prim_tests; stats6[4] = st.medium_probes; stats6[5] = st.nonfinite; }
+  return 0;
+}
+
+int emu_trace(void* p, const RtbRay* rays, long long n, unsigned flags, RtbHit* hits) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  for (long long i = 0; i < n; i++) {
+    Ray r;
+    r.ox = rays[i].origin[0]; r.oy = rays[i].origin[1]; r.oz = rays[i].origin[2];
+    r.dx = rays[i].direction[0]; r.dy = rays[i].direction[1]; r.dz = rays[i].direction[2];
+    r.time = (float)rays[i].time;
+    Hit best;
+    hit_reset(best);
+    if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, rays[i].t_min, best);
+    else if (S.n_surface_prims > 0) closest_surface<false>(S, r, rays[i].t_min, best, nullptr);
+    complete_hit(S, r, rays[i].time, best, hits[i]);
+  }
+  return 0;
+}
+
+int emu_medium_interval(void* p, int medium, const RtbRay* rays, long long n, double* t0, double* t1) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  for (long long i = 0; i < n; i++) {
+    Ray r;
+    r.ox = rays[i].origin[0]; r.oy = rays[i].origin[1]; r.oz = rays[i].origin[2];
+    r.dx = rays[i].direction[0]; r.dy = rays[i].direction[1]; r.dz = rays[i].direction[2];
+    r.time = (float)rays[i].time;
+    double a, b;
+    if (medium_interval(S, S.media[medium], r, a, b)) { t0[i] = a; t1[i] = b; } else { t0[i] = t1[i] = NAN; }
+  }
+  return 0;
+}
+
+int emu_eval_texture(void* p, int texture, const double* uvp, long long n, double* rgb) {
+  const DScene& S = static_cast<Emu*>(p)->dev;
+  for (long long i = 0; i < n; i++) {
+    const V3 c = texture_value(S, texture, (float)uvp[5 * i], (float)uvp[5 * i + 1], uvp[5 * i + 2], uvp[5 * i + 3], uvp[5 * i + 4]);
+    rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+  }
+  return 0;
+}
+
+int emu_eval_light_pdf(void* p, const double* od, long long n, double* pdf) {
+  const DScene& S = static_cast<Emu*>(p)->dev;
+  for (long long i = 0; i < n; i++) {
+    Ray probe;
+    probe.ox = od[6 * i]; probe.oy = od[6 * i + 1]; probe.oz = od[6 * i + 2];
+    probe.dx = od[6 * i + 3]; probe.dy = od[6 * i + 4]; probe.dz = od[6 * i + 5];
+    probe.time = 0.f;
+    double sum = 0.;
+    for (int k = 0; k < S.n_lights; k++) sum += light_pdf_one(S.lights[k], probe);
+    pdf[i] = sum * (1. / (double)S.n_lights);
+  }
+  return 0;
+}
+
+}  // extern "C"
