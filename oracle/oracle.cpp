@@ -63,7 +63,7 @@ inline Vec3 operator-(const Vec3& a) { return Vec3(-a.x, -a.y, -a.z); }
 inline Vec3 operator*(const Vec3& a, const Vec3& b) { return Vec3(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline Vec3 operator*(double t, const Vec3& a) { return Vec3(t * a.x, t * a.y, t * a.z); }
 inline Vec3 operator*(const Vec3& a, double t) { return t * a; }
-inline Vec3 operator/(const Vec3& a, double t) { return (1. / t) * a; }  // src/vec3.rs: v * (1/t)
+inline Vec3 operator/(const Vec3& a, double t) { return Vec3(a.x / t, a.y / t, a.z / t); }  // src/vec3.rs:145-151: true division
 
 inline double dot(const Vec3& u, const Vec3& v) { return u.x * v.x + u.y * v.y + u.z * v.z; }  // :167
 inline Vec3 cross(const Vec3& u, const Vec3& v) {                                              // :171

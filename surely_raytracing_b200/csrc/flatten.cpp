@@ -21,7 +21,8 @@ inline D3 operator*(double s, D3 a) { return {s * a.x, s * a.y, s * a.z}; }
 inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline D3 cross(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 inline double length(D3 a) { return std::sqrt(dot(a, a)); }
-inline D3 unit(D3 a) { return (1. / length(a)) * a; }
+inline D3 div(D3 a, double t) { return {a.x / t, a.y / t, a.z / t}; }  // Vec3 / f64 is a true division (src/vec3.rs:145-151)
+inline D3 unit(D3 a) { return div(a, length(a)); }
 
 // composed instance transform: p_world = R_y(theta) * p_obj + t, with the matrix convention of
 // RotateY::hit's "object -> world" step (src/transform.rs:113-127): x' = c x + s z, z' = -s x + c z
@@ -60,7 +61,7 @@ struct Builder {
     const D3 v = X.rot({o.v[6], o.v[7], o.v[8]});
     const D3 n = cross(u, v);
     const D3 normal = unit(n);
-    const D3 w = (1. / dot(n, n)) * n;
+    const D3 w = div(n, dot(n, n));
     const double dd = dot(normal, q);
     const D3 A = cross(v, w), B = cross(w, u);  // alpha = w.(p x v) = p.(v x w); beta = w.(u x p) = p.(w x u)
     const double p12[12] = {normal.x, normal.y, normal.z, dd, A.x, A.y, A.z, -dot(A, q), B.x, B.y, B.z, -dot(B, q)};
@@ -356,8 +357,8 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     const double viewport_width = viewport_height * (double)c.image_width / (double)image_height;
     const D3 w = unit(lookfrom - lookat), u = unit(cross(vup, w)), v = cross(w, u);
     const D3 viewport_u = viewport_width * u, viewport_v = viewport_height * ((-1.) * v);
-    const D3 du = (1. / (double)c.image_width) * viewport_u, dv = (1. / (double)image_height) * viewport_v;
-    const D3 upper_left = lookfrom - (focus_dist * w) - ((1. / 2.) * viewport_u) - ((1. / 2.) * viewport_v);
+    const D3 du = div(viewport_u, (double)c.image_width), dv = div(viewport_v, (double)image_height);
+    const D3 upper_left = lookfrom - (focus_dist * w) - div(viewport_u, 2.) - div(viewport_v, 2.);
     const D3 pixel00 = upper_left + 0.5 * (du + dv);
     const double defocus_radius = focus_dist * std::tan((c.defocus_angle / 2.) * (kPi / 180.));
     const int root = (int)std::sqrt((double)c.samples_per_pixel);

@@ -113,13 +113,13 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S,
   Ray r;
   r.ox = in.origin[0]; r.oy = in.origin[1]; r.oz = in.origin[2];
   r.dx = in.direction[0]; r.dy = in.direction[1]; r.dz = in.direction[2];
-  r.time = (float)in.time;
+  r.time = in.time;
   Hit best;
   hit_reset(best);
   if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, in.t_min, best);
   else if (S.n_surface_prims > 0) closest_surface<false>(S, r, in.t_min, best, nullptr);
   RtbHit out;
-  complete_hit(S, r, in.time, best, out);
+  complete_hit(S, r, best, out);
   hits[i] = out;
 }
 
@@ -138,7 +138,7 @@ __global__ void k_medium_interval(const __grid_constant__ DScene S, int medium, 
   Ray r;
   r.ox = in.origin[0]; r.oy = in.origin[1]; r.oz = in.origin[2];
   r.dx = in.direction[0]; r.dy = in.direction[1]; r.dz = in.direction[2];
-  r.time = (float)in.time;
+  r.time = in.time;
   double a, b;
   if (medium_interval(S, S.media[medium], r, a, b)) { t0[i] = a; t1[i] = b; }
   else { t0[i] = t1[i] = RTB_INF - RTB_INF; /* NaN */ }
@@ -172,7 +172,7 @@ __global__ void k_eval_light_pdf(const __grid_constant__ DScene S, const double*
   Ray probe;
   probe.ox = od[6 * i]; probe.oy = od[6 * i + 1]; probe.oz = od[6 * i + 2];
   probe.dx = od[6 * i + 3]; probe.dy = od[6 * i + 4]; probe.dz = od[6 * i + 5];
-  probe.time = 0.f;
+  probe.time = 0.;
   double sum = 0.;
   for (int k = 0; k < S.n_lights; k++) sum += light_pdf_one(S.lights[k], probe);
   pdf[i] = sum * (1. / (double)S.n_lights);

@@ -88,7 +88,7 @@ RTB_DEV V3 normalize(V3 a) { return rsqrtf(dot(a, a)) * a; }
 struct Ray {
   double ox, oy, oz;  // origin: f64 (hit points must stay on their surface to ~1e-13, like the reference)
   double dx, dy, dz;  // direction, not normalised (Q3); secondary directions are fp32-valued
-  float time;
+  double time;        // f64 so that the parity harness sees the reference's centre(time) exactly
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -164,7 +164,7 @@ RTB_DEV void test_prim(const DScene& S, int pi, const Ray& r, double tmin, Hit& 
   double t, a = 0., b = 0.;
   bool hit;
   if (kind == PRIM_QUAD) hit = quad_test(P, r, tmin, best.t, t, a, b);
-  else hit = sphere_test(P, info.x & PRIM_FLAG_MOVING, r, (double)r.time, tmin, best.t, t);
+  else hit = sphere_test(P, info.x & PRIM_FLAG_MOVING, r, r.time, tmin, best.t, t);
   if (hit && (t < best.t || tie_wins(kind, info.w, best.kind, best.id))) {
     best.t = t; best.a = a; best.b = b; best.prim = pi; best.kind = kind; best.id = info.w;
   }
@@ -410,7 +410,7 @@ RTB_DEV float lights_pdf_value(const DScene& S, double ox, double oy, double oz,
   Ray probe;
   probe.ox = ox; probe.oy = oy; probe.oz = oz;
   probe.dx = (double)dir.x; probe.dy = (double)dir.y; probe.dz = (double)dir.z;
-  probe.time = 0.f;  // Ray::new  src/ray.rs:20-26
+  probe.time = 0.;  // Ray::new  src/ray.rs:20-26
   double sum = 0.;
   for (int i = 0; i < S.n_lights; i++) sum += light_pdf_one(S.lights[i], probe);
   return (float)(sum * (1. / (double)S.n_lights));
@@ -440,7 +440,7 @@ RTB_DEV V3 lights_random(const DScene& S, double ox, double oy, double oz, float
 
 // full hit record of the winner, f64 (parity harness): Sphere::hit :168-183 / Quad::hit :477-489 and
 // the point/normal mapping of Translate/RotateY (already in world space here because instances are baked)
-RTB_DEV void complete_hit(const DScene& S, const Ray& r, double time64, const Hit& best, RtbHit& out) {
+RTB_DEV void complete_hit(const DScene& S, const Ray& r, const Hit& best, RtbHit& out) {
   out.prim = -1; out.front_face = 0; out.material = -1; out.reserved = 0;
   out.t = RTB_INF;
   out.p[0] = out.p[1] = out.p[2] = 0.; out.normal[0] = out.normal[1] = out.normal[2] = 0.;
@@ -456,7 +456,7 @@ RTB_DEV void complete_hit(const DScene& S, const Ray& r, double time64, const Hi
     u = best.a; v = best.b;
   } else {
     double cx = P[0].x, cy = P[0].y, cz = P[1].x;
-    if (info.x & PRIM_FLAG_MOVING) { cx += time64 * P[2].x; cy += time64 * P[2].y; cz += time64 * P[3].x; }
+    if (info.x & PRIM_FLAG_MOVING) { cx += r.time * P[2].x; cy += r.time * P[2].y; cz += r.time * P[3].x; }
     const double inv_r = 1. / P[1].y;
     nx = (px - cx) * inv_r; ny = (py - cy) * inv_r; nz = (pz - cz) * inv_r;
     const double2 cs = S.xforms[info.z];
@@ -503,7 +503,7 @@ RTB_DEV void generate_primary(const DScene& S, uint32_t pixel, uint32_t sample, 
   }
   ps.ray.ox = ox; ps.ray.oy = oy; ps.ray.oz = oz;
   ps.ray.dx = sx - ox; ps.ray.dy = sy - oy; ps.ray.dz = sz - oz;
-  ps.ray.time = u.z;  // :233
+  ps.ray.time = (double)u.z;  // :233
   ps.bx = ps.by = ps.bz = 1.f;
   ps.pixel = pixel; ps.sample = sample; ps.bounce = 0;
 }
@@ -565,7 +565,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
       double cx = c01.x, cy = c01.y, cz = c2r.x;
       if (info.x & PRIM_FLAG_MOVING) {
         const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
-        cx += (double)r.time * v01.x; cy += (double)r.time * v01.y; cz += (double)r.time * v2.x;
+        cx += r.time * v01.x; cy += r.time * v01.y; cz += r.time * v2.x;
       }
       const double inv_r = 1. / c2r.y;
       const double nx = (px - cx) * inv_r, ny = (py - cy) * inv_r, nz = (pz - cz) * inv_r;  // object.rs:169

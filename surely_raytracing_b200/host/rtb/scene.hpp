@@ -45,7 +45,7 @@ inline Vec3 operator-(const Vec3& a) { return Vec3(-a.x_, -a.y_, -a.z_); }
 inline Vec3 operator*(const Vec3& a, const Vec3& b) { return Vec3(a.x_ * b.x_, a.y_ * b.y_, a.z_ * b.z_); }
 inline Vec3 operator*(double t, const Vec3& a) { return Vec3(t * a.x_, t * a.y_, t * a.z_); }
 inline Vec3 operator*(const Vec3& a, double t) { return t * a; }
-inline Vec3 operator/(const Vec3& a, double t) { return (1. / t) * a; }
+inline Vec3 operator/(const Vec3& a, double t) { return Vec3(a.x_ / t, a.y_ / t, a.z_ / t); }  // true division, vec3.rs:145-151
 inline Vec3 unit_vector(const Vec3& v) { return v / v.length(); }
 
 // ---- utils.rs: host-side construction randomness ----------------------------------------------

@@ -92,12 +92,12 @@ int emu_trace(void* p, const RtbRay* rays, long long n, unsigned flags, RtbHit* 
     Ray r;
     r.ox = rays[i].origin[0]; r.oy = rays[i].origin[1]; r.oz = rays[i].origin[2];
     r.dx = rays[i].direction[0]; r.dy = rays[i].direction[1]; r.dz = rays[i].direction[2];
-    r.time = (float)rays[i].time;
+    r.time = rays[i].time;
     Hit best;
     hit_reset(best);
     if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, rays[i].t_min, best);
     else if (S.n_surface_prims > 0) closest_surface<false>(S, r, rays[i].t_min, best, nullptr);
-    complete_hit(S, r, rays[i].time, best, hits[i]);
+    complete_hit(S, r, best, hits[i]);
   }
   return 0;
 }
@@ -109,7 +109,7 @@ int emu_medium_interval(void* p, int medium, const RtbRay* rays, long long n, do
     Ray r;
     r.ox = rays[i].origin[0]; r.oy = rays[i].origin[1]; r.oz = rays[i].origin[2];
     r.dx = rays[i].direction[0]; r.dy = rays[i].direction[1]; r.dz = rays[i].direction[2];
-    r.time = (float)rays[i].time;
+    r.time = rays[i].time;
     double a, b;
     if (medium_interval(S, S.media[medium], r, a, b)) { t0[i] = a; t1[i] = b; } else { t0[i] = t1[i] = NAN; }
   }
@@ -131,7 +131,7 @@ int emu_eval_light_pdf(void* p, const double* od, long long n, double* pdf) {
     Ray probe;
     probe.ox = od[6 * i]; probe.oy = od[6 * i + 1]; probe.oz = od[6 * i + 2];
     probe.dx = od[6 * i + 3]; probe.dy = od[6 * i + 4]; probe.dz = od[6 * i + 5];
-    probe.time = 0.f;
+    probe.time = 0.;
     double sum = 0.;
     for (int k = 0; k < S.n_lights; k++) sum += light_pdf_one(S.lights[k], probe);
     pdf[i] = sum * (1. / (double)S.n_lights);

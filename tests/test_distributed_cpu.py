@@ -1,0 +1,75 @@
+"""world_size-2 gloo test of the multi-GPU plumbing on CPU: sample split + one sum-reduce.
+The renderer here is the oracle in KEYED mode (the CUDA library needs a GPU); what is under test is
+the partition / reduce logic of surely_raytracing_b200.distributed that bench.py uses with NCCL."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from surely_raytracing_b200.distributed import pass_rows, split_samples
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_split_is_a_partition():
+    for spp in (1, 49, 961, 1936, 10000):
+        for world in (1, 2, 3, 4, 8):
+            parts = [split_samples(spp, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == spp
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        split_samples(10, 2, 2)
+
+
+def test_pass_rows_cover_the_grid_once_per_cycle():
+    for world in (1, 2, 4, 8):
+        seen = set()
+        steps = 100 // world if 100 % world == 0 else None
+        if steps is None:
+            continue
+        for k in range(steps):
+            for r in range(world):
+                lo, hi = pass_rows(k, world, r, 100)
+                assert hi - lo == 100 and lo % 100 == 0
+                seen.add(lo)
+        assert len(seen) == 100
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from oracle import orc
+    from surely_raytracing_b200.distributed import reduce_to_root, split_samples
+    from surely_raytracing_b200.scenes import BuiltScene
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = orc.OracleScene(BuiltScene("c2", width=40, spp=25))
+    lo, hi = split_samples(o.info.spp_used, world, rank)
+    s, _ = o.render(lo, hi, sampler=orc.SAMPLER_KEYED, threads=1)
+    accum = torch.from_numpy(s.astype(np.float32))      # fp32 accumulation buffers, like the GPU path
+    reduce_to_root(accum, 0)
+    if rank == 0:
+        np.save(out_path, accum.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_split_and_reduce_equals_single_rank(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import orc
+    from surely_raytracing_b200.scenes import BuiltScene
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "reduced.npy"
+    mp.spawn(_worker, args=(2, port, str(out)), nprocs=2, join=True)
+    got = np.load(out)
+    o = orc.OracleScene(BuiltScene("c2", width=40, spp=25))
+    full, _ = o.render(sampler=orc.SAMPLER_KEYED, threads=1)
+    assert np.allclose(got, full, rtol=1e-6, atol=1e-5)
