@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "librtb200.so"
+LIB_PATH = Path(os.environ.get("RTB200_LIB", PKG_DIR / "librtb200.so"))  # override: debug builds only
 SCENES_LIB_PATH = PKG_DIR / "librtb_scenes.so"
 
 RTB_ABI_VERSION = 1

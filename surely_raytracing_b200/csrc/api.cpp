@@ -286,8 +286,9 @@ int rtb_trace(rtb_scene* s, const RtbRay* rays, int64_t n, uint32_t flags, RtbHi
   CU(cudaSetDevice(s->device));
   CU(s->scratch_a.reserve((size_t)n * sizeof(RtbRay)));
   CU(s->scratch_b.reserve((size_t)n * sizeof(RtbHit)));
+  CU(s->scratch_c.reserve(trace_scratch_bytes(n)));
   CU(cudaMemcpy(s->scratch_a.p, rays, (size_t)n * sizeof(RtbRay), cudaMemcpyHostToDevice));
-  CU(launch_trace(s->dev, static_cast<const RtbRay*>(s->scratch_a.p), n, flags, static_cast<RtbHit*>(s->scratch_b.p), nullptr, 0));
+  CU(launch_trace(s->dev, static_cast<const RtbRay*>(s->scratch_a.p), n, flags, static_cast<RtbHit*>(s->scratch_b.p), s->scratch_c.p, 0));
   CU(cudaMemcpy(hits, s->scratch_b.p, (size_t)n * sizeof(RtbHit), cudaMemcpyDeviceToHost));
   return RTB_OK;
 }

@@ -3,7 +3,7 @@
 //
 //   nodes      float4[4*n_nodes]   BVH2, one 64 B record per inner node holding BOTH children's
 //                                  boxes (fp32, padded outward so the fp32 slab test is conservative)
-//   prims      double2[6*n_prims]  96 B per primitive in BVH-leaf order, f64, world space (instance
+//   prims      double2[8*n_prims]  128 B per primitive in BVH-leaf order, f64, world space (instance
 //                                  transforms baked in); surfaces first, then medium-boundary prims
 //   prim_info  int4[n_prims]       {kind, material, xform, canonical id}
 //   xforms     double2[n_xforms]   {cos, sin} of the composed rotate_y of an instance chain (uv only)
@@ -34,11 +34,12 @@ enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
 constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
 constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf (leaf ref = ~((first << 3) | (count - 1)))
 
-// primitive payload, 12 doubles (6 x double2):
-//   SPHERE: cx cy | cz r | cvx cvy | cvz - | - - | - -           (center(t) = c + t * cv)
-//   QUAD  : nx ny | nz d | Ax Ay | Az a0 | Bx By | Bz b0         (alpha = A.p + a0, beta = B.p + b0;
-//           n = unit normal, d = n.q, A = v x w, B = w x u, a0 = -A.q, b0 = -B.q, w = n/(n.n))
-constexpr int PRIM_D2 = 6;
+// primitive payload, 16 doubles (8 x double2 = 128 B), the fields of the reference structs:
+//   SPHERE: cx cy | cz r | cvx cvy | cvz - | ...                 (center(t) = c + t * cv, src/object.rs:74-80)
+//   QUAD  : nx ny | nz d | qx qy | qz ux | uy uz | vx vy | vz wx | wy wz     (src/object.rs:415-425:
+//           n = unit normal, d = n.q, w = n/(n.n)); the test evaluates Quad::hit operation by operation
+constexpr int PRIM_D2 = 8;
+constexpr int PRIM_DOUBLES = 2 * PRIM_D2;
 
 struct DMaterial {
   int kind;
@@ -65,13 +66,14 @@ struct DMedium {
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
 };
 
-struct DLight {
-  int kind;
-  int pad;
-  double prim[12];  // same payload as `prims` (world space, time 0)
+struct alignas(16) DLight {
+  double prim[16];  // same payload as `prims` (world space, time 0); first + 16-aligned: read as double2
   double q[3], u[3], v[3];  // QUAD: sampling frame
   double area;
+  int kind;
+  int pad;
 };
+static_assert(sizeof(DLight) % 16 == 0, "DLight records must keep prim[] 16-byte aligned");
 
 struct DCamera {
   double center[3], pixel00[3], du[3], dv[3], disk_u[3], disk_v[3];

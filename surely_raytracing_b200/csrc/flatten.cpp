@@ -36,7 +36,7 @@ struct Xform {
 
 struct Baked {
   int kind, flags, material, xform, id;
-  double payload[12];
+  double payload[PRIM_DOUBLES];
   double lo[3], hi[3];
 };
 
@@ -63,9 +63,8 @@ struct Builder {
     const D3 normal = unit(n);
     const D3 w = div(n, dot(n, n));
     const double dd = dot(normal, q);
-    const D3 A = cross(v, w), B = cross(w, u);  // alpha = w.(p x v) = p.(v x w); beta = w.(u x p) = p.(w x u)
-    const double p12[12] = {normal.x, normal.y, normal.z, dd, A.x, A.y, A.z, -dot(A, q), B.x, B.y, B.z, -dot(B, q)};
-    std::memcpy(b.payload, p12, sizeof(p12));
+    const double p16[PRIM_DOUBLES] = {normal.x, normal.y, normal.z, dd, q.x, q.y, q.z, u.x, u.y, u.z, v.x, v.y, v.z, w.x, w.y, w.z};
+    std::memcpy(b.payload, p16, sizeof(p16));
     const D3 c[4] = {q, q + u, q + v, q + u + v};
     for (int a = 0; a < 3; a++) { b.lo[a] = kInf; b.hi[a] = -kInf; }
     for (const D3& p : c) {
@@ -81,8 +80,8 @@ struct Builder {
     const D3 cv = X.rot({o.v[4], o.v[5], o.v[6]});
     const bool moving = o.v[7] != 0.;
     const double r = o.v[3];
-    const double p12[12] = {c.x, c.y, c.z, r, cv.x, cv.y, cv.z, 0., 0., 0., 0., 0.};
-    std::memcpy(b.payload, p12, sizeof(p12));
+    const double p16[PRIM_DOUBLES] = {c.x, c.y, c.z, r, cv.x, cv.y, cv.z, 0., 0., 0., 0., 0., 0., 0., 0., 0.};
+    std::memcpy(b.payload, p16, sizeof(p16));
     const double ar = std::fabs(r);
     const double cc[3] = {c.x, c.y, c.z}, vv[3] = {cv.x, cv.y, cv.z};
     for (int a = 0; a < 3; a++) {
@@ -117,7 +116,7 @@ struct Builder {
         b.material = o.material;
         b.xform = xform_id(X);
         b.id = next_id++;
-        for (int a = 0; a < 12; a++)
+        for (int a = 0; a < PRIM_DOUBLES; a++)
           if (!std::isfinite(b.payload[a])) return fail("non-finite primitive (degenerate quad or bad coordinates)");
         (medium >= 0 ? boundaries[medium] : surfaces).push_back(b);
         return true;
@@ -232,7 +231,7 @@ inline float round_down(double x) { float f = (float)x; return ((double)f > x) ?
 inline float round_up(double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; }
 
 void emit_prim(HostScene& out, const Baked& b) {
-  out.prims.insert(out.prims.end(), b.payload, b.payload + 12);
+  out.prims.insert(out.prims.end(), b.payload, b.payload + PRIM_DOUBLES);
   out.prim_info.push_back(int4{b.kind | b.flags, b.material, b.xform, b.id});
 }
 

@@ -16,7 +16,7 @@ namespace rtb {
 
 struct HostScene {
   std::vector<float4> nodes;        // 4 per inner node
-  std::vector<double> prims;        // 12 per primitive (BVH order; surfaces, then boundaries)
+  std::vector<double> prims;        // PRIM_DOUBLES per primitive (BVH order; surfaces, then boundaries)
   std::vector<int4> prim_info;
   std::vector<double2> xforms;
   std::vector<DMedium> media;

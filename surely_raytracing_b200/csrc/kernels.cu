@@ -105,28 +105,57 @@ cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_
 // ------------------------------------------------------------------------------------------------
 // deterministic parity harness
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S, const RtbRay* __restrict__ rays,
-                                               long long n, uint32_t flags, RtbHit* __restrict__ hits) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const RtbRay in = rays[i];
+// Two kernels: (1) closest hit -> compact record {prim, t, alpha, beta}; (2) completion of the full
+// f64 hit record (point, normal, uv, face) for the winners.
+struct TraceHit { double t, a, b; int prim, pad; };
+
+__device__ __forceinline__ Ray load_ray(const RtbRay& in) {
   Ray r;
   r.ox = in.origin[0]; r.oy = in.origin[1]; r.oz = in.origin[2];
   r.dx = in.direction[0]; r.dy = in.direction[1]; r.dz = in.direction[2];
   r.time = in.time;
+  return r;
+}
+
+__global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene S, const RtbRay* __restrict__ rays,
+                                                       long long n, uint32_t flags, TraceHit* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RtbRay in = rays[i];
+  const Ray r = load_ray(in);
   Hit best;
   hit_reset(best);
   if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, in.t_min, best);
   else if (S.n_surface_prims > 0) closest_surface<false>(S, r, in.t_min, best, nullptr);
+  TraceHit h;
+  h.t = best.t; h.a = best.a; h.b = best.b; h.prim = best.prim; h.pad = 0;
+  out[i] = h;
+}
+
+__global__ void __launch_bounds__(128) k_trace_complete(const __grid_constant__ DScene S, const RtbRay* __restrict__ rays,
+                                                        long long n, const TraceHit* __restrict__ closest,
+                                                        RtbHit* __restrict__ hits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Ray r = load_ray(rays[i]);
+  const TraceHit h = closest[i];
+  Hit best;
+  best.t = h.t; best.a = h.a; best.b = h.b; best.prim = h.prim; best.kind = -1; best.id = -1;
   RtbHit out;
   complete_hit(S, r, best, out);
   hits[i] = out;
 }
 
-cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits, const int*,
-                         cudaStream_t stream) {
+size_t trace_scratch_bytes(int64_t n) { return (size_t)n * sizeof(TraceHit); }
+
+cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits,
+                         void* d_scratch, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  k_trace<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, d_rays, n, flags, d_hits);
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  k_trace_closest<<<blocks, 128, 0, stream>>>(S, d_rays, n, flags, static_cast<TraceHit*>(d_scratch));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_trace_complete<<<blocks, 128, 0, stream>>>(S, d_rays, n, static_cast<const TraceHit*>(d_scratch), d_hits);
   return cudaGetLastError();
 }
 

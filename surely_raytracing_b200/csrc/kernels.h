@@ -20,8 +20,9 @@ cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_
                                     bool collect_stats, void* d_workspace, size_t workspace_bytes,
                                     int64_t paths_per_wave, cudaStream_t stream, int* launches);
 
+size_t trace_scratch_bytes(int64_t n);
 cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits,
-                         const int* d_material_of_prim_unused, cudaStream_t stream);
+                         void* d_scratch, cudaStream_t stream);
 cudaError_t launch_medium_interval(const DScene& S, int medium, const RtbRay* d_rays, int64_t n, double* d_t0,
                                    double* d_t1, cudaStream_t stream);
 cudaError_t launch_eval_texture(const DScene& S, int texture, const double* d_uvp, int64_t n, double* d_rgb,

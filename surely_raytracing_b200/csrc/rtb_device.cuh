@@ -20,6 +20,13 @@
 #include "../../include/rtb200.h"
 #include "device_scene.h"
 
+#if defined(RTB_DEBUG_BOUNDS)
+#include <assert.h>
+#define RTB_ASSERT(c) assert(c)
+#else
+#define RTB_ASSERT(c) ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 #define RTB_DEV __device__ __forceinline__
 #define RTB_LDG(p) __ldg(p)
@@ -85,6 +92,27 @@ RTB_DEV float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z))
 RTB_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RTB_DEV V3 normalize(V3 a) { return rsqrtf(dot(a, a)) * a; }
 
+// ------------------------------------------------------------------------------------------------
+// f64 arithmetic WITHOUT fused multiply-add, in the reference's operation order.  The reference is
+// compiled Rust: `a*b + c` is two roundings.  Symmetric scenes put primary rays exactly on shared
+// quad edges (the Cornell camera sends its diagonal pixels through the wall/floor corner), where the
+// inside test `a < 0` is decided by the last bit -- so the primitive tests mirror the reference's
+// arithmetic operation by operation (nvcc would otherwise contract to DFMA).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+RTB_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+RTB_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+RTB_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+RTB_DEV double dmul(double a, double b) { return a * b; }   // host build: -ffp-contract=off
+RTB_DEV double dadd(double a, double b) { return a + b; }
+RTB_DEV double dsub(double a, double b) { return a - b; }
+#endif
+// dot(u, v) = u.x*v.x + u.y*v.y + u.z*v.z, left to right  (src/vec3.rs:167-169)
+RTB_DEV double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+  return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));
+}
+
 struct Ray {
   double ox, oy, oz;  // origin: f64 (hit points must stay on their surface to ~1e-13, like the reference)
   double dx, dy, dz;  // direction, not normalised (Q3); secondary directions are fp32-valued
@@ -96,45 +124,55 @@ struct Ray {
 // tie rule); lower bound closed for quads (Interval::contains) and open for spheres
 // (Interval::surrounds) -- src/object.rs:161-163, 462, src/interval.rs:21-27 (Q4).
 // ------------------------------------------------------------------------------------------------
-// Quad::hit  src/object.rs:453-490, with alpha/beta through the precomputed A = v x w, B = w x u
+// Quad::hit  src/object.rs:453-490, operation by operation (payload: normal d | q | u | v | w)
 RTB_DEV bool quad_test(const double2* __restrict__ P, const Ray& r, double tmin, double tmax, double& t_out,
                        double& a_out, double& b_out) {
   const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
-  const double denom = n01.x * r.dx + n01.y * r.dy + n2d.x * r.dz;
+  const double denom = ddot(n01.x, n01.y, n2d.x, r.dx, r.dy, r.dz);
   if (fabs(denom) < 1e-8) return false;
-  const double t = (n2d.y - (n01.x * r.ox + n01.y * r.oy + n2d.x * r.oz)) / denom;
+  const double t = dsub(n2d.y, ddot(n01.x, n01.y, n2d.x, r.ox, r.oy, r.oz)) / denom;
   if (!(tmin <= t && t <= tmax)) return false;
-  const double px = r.ox + t * r.dx, py = r.oy + t * r.dy, pz = r.oz + t * r.dz;
-  const double2 A01 = RTB_LDG(P + 2), A2a = RTB_LDG(P + 3);
-  const double a = A01.x * px + A01.y * py + A2a.x * pz + A2a.y;
+  const double2 q01 = RTB_LDG(P + 2), q2u0 = RTB_LDG(P + 3), u12 = RTB_LDG(P + 4);
+  const double2 v01 = RTB_LDG(P + 5), v2w0 = RTB_LDG(P + 6), w12 = RTB_LDG(P + 7);
+  // intersection = r.at(t); planar_hitpt_vector = intersection - q
+  const double hx = dsub(dadd(r.ox, dmul(t, r.dx)), q01.x);
+  const double hy = dsub(dadd(r.oy, dmul(t, r.dy)), q01.y);
+  const double hz = dsub(dadd(r.oz, dmul(t, r.dz)), q2u0.x);
+  const double ux = q2u0.y, uy = u12.x, uz = u12.y, vx = v01.x, vy = v01.y, vz = v2w0.x;
+  const double wx = v2w0.y, wy = w12.x, wz = w12.y;
+  // a = dot(w, cross(hp, v))
+  const double a = ddot(wx, wy, wz, dsub(dmul(hy, vz), dmul(hz, vy)), dsub(dmul(hz, vx), dmul(hx, vz)),
+                        dsub(dmul(hx, vy), dmul(hy, vx)));
   if ((a < 0.) || (1. < a)) return false;
-  const double2 B01 = RTB_LDG(P + 4), B2b = RTB_LDG(P + 5);
-  const double b = B01.x * px + B01.y * py + B2b.x * pz + B2b.y;
+  // b = dot(w, cross(u, hp))
+  const double b = ddot(wx, wy, wz, dsub(dmul(uy, hz), dmul(uz, hy)), dsub(dmul(uz, hx), dmul(ux, hz)),
+                        dsub(dmul(ux, hy), dmul(uy, hx)));
   if ((b < 0.) || (1. < b)) return false;
   t_out = t; a_out = a; b_out = b;
   return true;
 }
 
-// Sphere::hit  src/object.rs:145-166 (root selection only; normal/uv are completed for the winner)
+// Sphere::hit  src/object.rs:145-166, operation by operation (root selection only; normal/uv are
+// completed for the winner).  payload: cx cy | cz r | cvx cvy | cvz -
 RTB_DEV bool sphere_test(const double2* __restrict__ P, int moving, const Ray& r, double time, double tmin, double tmax,
                          double& t_out) {
   const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
   double cx = c01.x, cy = c01.y, cz = c2r.x;
-  if (moving) {  // Sphere::center  src/object.rs:107-112
+  if (moving) {  // Sphere::center  src/object.rs:107-112: self.center + time * dir
     const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
-    cx += time * v01.x; cy += time * v01.y; cz += time * v2.x;
+    cx = dadd(cx, dmul(time, v01.x)); cy = dadd(cy, dmul(time, v01.y)); cz = dadd(cz, dmul(time, v2.x));
   }
-  const double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
-  const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
-  const double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
-  const double c = (ocx * ocx + ocy * ocy + ocz * ocz) - c2r.y * c2r.y;
-  const double disc = half_b * half_b - a * c;
+  const double ocx = dsub(r.ox, cx), ocy = dsub(r.oy, cy), ocz = dsub(r.oz, cz);
+  const double a = ddot(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+  const double half_b = ddot(ocx, ocy, ocz, r.dx, r.dy, r.dz);
+  const double c = dsub(ddot(ocx, ocy, ocz, ocx, ocy, ocz), dmul(c2r.y, c2r.y));
+  const double disc = dsub(dmul(half_b, half_b), dmul(a, c));
   if (disc < 0.) return false;
   const double sqrtd = sqrt(disc);
-  double root = (-half_b - sqrtd) / a;
+  double root = dsub(-half_b, sqrtd) / a;
   if (!(tmin < root && root <= tmax)) {
     if (root > tmax) return false;  // the far root is even larger
-    root = (sqrtd - half_b) / a;
+    root = dsub(sqrtd, half_b) / a;
     if (!(tmin < root && root <= tmax)) return false;
   }
   t_out = root;
@@ -158,6 +196,7 @@ struct Hit {
 RTB_DEV void hit_reset(Hit& h) { h.t = RTB_INF; h.a = 0.; h.b = 0.; h.prim = -1; h.kind = -1; h.id = -1; }
 
 RTB_DEV void test_prim(const DScene& S, int pi, const Ray& r, double tmin, Hit& best) {
+  RTB_ASSERT(pi >= 0 && pi < S.n_prims);
   const int4 info = RTB_LDG(S.prim_info + pi);
   const double2* P = S.prims + (size_t)pi * PRIM_D2;
   const int kind = info.x & 0xFF;
@@ -186,6 +225,7 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
   for (;;) {
     if (node >= 0) {
       if (STATS) st->node_visits++;
+      RTB_ASSERT(node < S.n_nodes);
       const float4* N = S.nodes + 4 * (size_t)node;
       const float4 n0 = RTB_LDG(N + 0), n1 = RTB_LDG(N + 1), n2 = RTB_LDG(N + 2), n3 = RTB_LDG(N + 3);
       // fminf/fmaxf drop NaNs (0 * inf when the origin sits on a slab plane of a parallel ray)
@@ -204,6 +244,7 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
       int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
       if (h0 && h1) {
         if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
+        RTB_ASSERT(sp < BVH_STACK);
         stack[sp++] = ch1;
         node = ch0;
         continue;
@@ -446,23 +487,27 @@ RTB_DEV void complete_hit(const DScene& S, const Ray& r, const Hit& best, RtbHit
   out.p[0] = out.p[1] = out.p[2] = 0.; out.normal[0] = out.normal[1] = out.normal[2] = 0.;
   out.u = out.v = 0.;
   if (best.prim < 0) return;
+  RTB_ASSERT(best.prim < S.n_prims);
   const int4 info = RTB_LDG(S.prim_info + best.prim);
+  RTB_ASSERT(info.z >= 0 && info.z < 64);
   const double2* P = S.prims + (size_t)best.prim * PRIM_D2;
   const double t = best.t;
-  const double px = r.ox + t * r.dx, py = r.oy + t * r.dy, pz = r.oz + t * r.dz;
+  const double px = dadd(r.ox, dmul(t, r.dx)), py = dadd(r.oy, dmul(t, r.dy)), pz = dadd(r.oz, dmul(t, r.dz));  // Ray::at
   double nx, ny, nz, u, v;
   if ((info.x & 0xFF) == PRIM_QUAD) {
     nx = P[0].x; ny = P[0].y; nz = P[1].x;
     u = best.a; v = best.b;
   } else {
     double cx = P[0].x, cy = P[0].y, cz = P[1].x;
-    if (info.x & PRIM_FLAG_MOVING) { cx += r.time * P[2].x; cy += r.time * P[2].y; cz += r.time * P[3].x; }
-    const double inv_r = 1. / P[1].y;
-    nx = (px - cx) * inv_r; ny = (py - cy) * inv_r; nz = (pz - cz) * inv_r;
+    if (info.x & PRIM_FLAG_MOVING) {
+      cx = dadd(cx, dmul(r.time, P[2].x)); cy = dadd(cy, dmul(r.time, P[2].y)); cz = dadd(cz, dmul(r.time, P[3].x));
+    }
+    const double rad = P[1].y;  // (p - center) / radius is a true division (src/vec3.rs:145-151)
+    nx = dsub(px, cx) / rad; ny = dsub(py, cy) / rad; nz = dsub(pz, cz) / rad;
     const double2 cs = S.xforms[info.z];
     sphere_uv(cs.x * nx - cs.y * nz, ny, cs.y * nx + cs.x * nz, u, v);
   }
-  const bool front = (r.dx * nx + r.dy * ny + r.dz * nz) < 0.;
+  const bool front = ddot(r.dx, r.dy, r.dz, nx, ny, nz) < 0.;
   if (!front) { nx = -nx; ny = -ny; nz = -nz; }
   out.prim = info.w; out.front_face = front ? 1 : 0; out.material = info.y;
   out.t = t; out.p[0] = px; out.p[1] = py; out.p[2] = pz;
@@ -542,7 +587,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
     Lr += ps.bx * S.cam.background[0]; Lg += ps.by * S.cam.background[1]; Lb += ps.bz * S.cam.background[2];
     return false;
   }
-  const double px = r.ox + ev.t * r.dx, py = r.oy + ev.t * r.dy, pz = r.oz + ev.t * r.dz;  // Ray::at
+  const double px = dadd(r.ox, dmul(ev.t, r.dx)), py = dadd(r.oy, dmul(ev.t, r.dy)), pz = dadd(r.oz, dmul(ev.t, r.dz));  // Ray::at
   V3 n;
   bool front = true;
   float tu = 0.f, tv = 0.f;
@@ -557,7 +602,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
     const int needs_uv = S.materials[mat_id].needs_uv;
     if ((info.x & 0xFF) == PRIM_QUAD) {
       const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
-      front = (r.dx * n01.x + r.dy * n01.y + r.dz * n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
+      front = ddot(r.dx, r.dy, r.dz, n01.x, n01.y, n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
       n = v3((float)n01.x, (float)n01.y, (float)n2d.x);
       tu = (float)ev.a; tv = (float)ev.b;
     } else {

@@ -16,7 +16,7 @@ def build(force=False):
     srcs = [EMU_DIR / "emu.cpp", ROOT / "surely_raytracing_b200/csrc/flatten.cpp", ROOT / "surely_raytracing_b200/csrc/rtb_device.cuh",
             ROOT / "surely_raytracing_b200/csrc/device_scene.h", ROOT / "surely_raytracing_b200/csrc/flatten.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", str(LIB),
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", str(LIB),
                         str(srcs[0]), str(srcs[1])], check=True, capture_output=True)
 
 
