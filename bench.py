@@ -249,6 +249,8 @@ def run_b200(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - wall0) * 1e3
     step_ms = [starts[k].elapsed_time(stops[k]) for k in range(args.steps)]
     reduce_ms = starts[-1].elapsed_time(stops[-1]) if world > 1 else 0.0
+    if rank == 0:
+        print("step_ms", [round(x, 2) for x in step_ms], file=sys.stderr)
     timed_ms = sum(step_ms) + reduce_ms
     t = torch.tensor([timed_ms], dtype=torch.float64, device=dev)
     if world > 1:

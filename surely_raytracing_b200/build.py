@@ -43,7 +43,7 @@ def _run(cmd, verbose):
 
 def build_cuda_library(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
     out = PKG / "librtb200.so"
-    srcs = [CSRC / "kernels.cu", CSRC / "api.cpp", CSRC / "flatten.cpp"]
+    srcs = [CSRC / "kernels.cu", CSRC / "wavefront.cu", CSRC / "api.cpp", CSRC / "flatten.cpp"]
     deps = srcs + [CSRC / "rtb_device.cuh", CSRC / "device_scene.h", CSRC / "kernels.h", CSRC / "flatten.h",
                    PKG.parent / "include" / "rtb200.h"]
     if force or _stale(out, deps):

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,12 +77,15 @@ struct rtb_scene {
   DeviceBuffer scratch_c;
   DeviceBuffer workspace;  // wavefront queues
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  WavefrontContext wf{};
+  bool wf_ready = false;
   RtbStats last{};
   bool stats_pending = false;
   ~rtb_scene() {
     for (void* p : owned) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (wf_ready) wavefront_context_destroy(&wf);
   }
 };
 
@@ -184,7 +188,15 @@ static int check_range(const rtb_scene* s, const RtbRenderParams* p) {
   return RTB_OK;
 }
 
-static const int64_t kWavefrontPaths = 1 << 20;
+// path slots in flight of the wavefront pipeline (RTB_WF_CAPACITY overrides, for tuning runs)
+static int64_t wavefront_capacity() {
+  static int64_t cap = [] {
+    const char* e = getenv("RTB_WF_CAPACITY");
+    long long v = e ? atoll(e) : 0;
+    return (int64_t)(v >= 1024 ? v : (1 << 22));
+  }();
+  return cap;
+}
 
 static int render_into(rtb_scene* s, const RtbRenderParams* p, float4* d_accum, cudaStream_t stream) {
   CU(cudaSetDevice(s->device));
@@ -194,11 +206,16 @@ static int render_into(rtb_scene* s, const RtbRenderParams* p, float4* d_accum, 
   int launches = 0;
   CU(cudaEventRecord(s->ev0, stream));
   if (p->sample_end > p->sample_begin) {
-    if (p->pipeline == RTB_PIPELINE_WAVEFRONT) {
-      const size_t ws = wavefront_workspace_bytes(s->dev, kWavefrontPaths);
+    if (p->pipeline != RTB_PIPELINE_MEGAKERNEL) {  // default = wavefront
+      const int64_t cap = wavefront_capacity();
+      const size_t ws = wavefront_workspace_bytes(s->dev, cap);
       CU(s->workspace.reserve(ws));
-      CU(launch_render_wavefront(s->dev, p->sample_begin, p->sample_end, d_accum, d_stats, collect, s->workspace.p,
-                                 s->workspace.bytes, kWavefrontPaths, stream, &launches));
+      if (!s->wf_ready) {
+        CU(wavefront_context_create(&s->wf));
+        s->wf_ready = true;
+      }
+      CU(launch_render_wavefront(s->dev, s->wf, p->sample_begin, p->sample_end, d_accum, d_stats, collect, s->workspace.p,
+                                 s->workspace.bytes, cap, stream, &launches));
     } else {
       CU(launch_render_mega(s->dev, p->sample_begin, p->sample_end, d_accum, d_stats, collect, stream, &launches));
     }

@@ -27,6 +27,12 @@ namespace rtb {
 
 enum : int { PRIM_SPHERE = 0, PRIM_QUAD = 1 };
 enum : int { PRIM_FLAG_MOVING = 0x100 };
+// shading class of the material behind a primitive / medium (bits 16..19 of prim_info.x): the sort key
+// of the wavefront shade stage.  Lambertian is split by texture so that the expensive Perlin
+// evaluation and the cheap solid colour never share a warp.
+enum : int { CLS_MISS = 0, CLS_LIGHT = 1, CLS_LAMBERT_SOLID = 2, CLS_LAMBERT_TEX = 3, CLS_METAL = 4, CLS_DIELECTRIC = 5,
+             CLS_ISOTROPIC = 6, CLS_NOISE = 7, NUM_CLASSES = 8 };
+constexpr int PRIM_CLASS_SHIFT = 16;
 enum : int { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
 enum : int { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_IMAGE = 2, TEX_NOISE = 3 };
 enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
@@ -61,7 +67,7 @@ struct DTexture {
 struct DMedium {
   int first_prim, n_prims;  // boundary primitives (in `prims`, after the surfaces), DFS order
   int material;
-  int pad;
+  int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere
   double neg_inv_density;
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
 };

@@ -230,9 +230,23 @@ struct BvhBuilder {
 inline float round_down(double x) { float f = (float)x; return ((double)f > x) ? std::nextafterf(f, -INFINITY) : f; }
 inline float round_up(double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; }
 
-void emit_prim(HostScene& out, const Baked& b) {
+int shading_class(const RtbSceneDesc& d, int material) {
+  const RtbMaterial& m = d.materials[material];
+  switch (m.kind) {
+    case RTB_MAT_DIFFUSE_LIGHT: return CLS_LIGHT;
+    case RTB_MAT_METAL: return CLS_METAL;
+    case RTB_MAT_DIELECTRIC: return CLS_DIELECTRIC;
+    case RTB_MAT_ISOTROPIC: return CLS_ISOTROPIC;
+    default: {
+      const int tk = d.textures[m.texture].kind;
+      return tk == RTB_TEX_SOLID ? CLS_LAMBERT_SOLID : (tk == RTB_TEX_NOISE ? CLS_NOISE : CLS_LAMBERT_TEX);
+    }
+  }
+}
+
+void emit_prim(const RtbSceneDesc& d, HostScene& out, const Baked& b) {
   out.prims.insert(out.prims.end(), b.payload, b.payload + PRIM_DOUBLES);
-  out.prim_info.push_back(int4{b.kind | b.flags, b.material, b.xform, b.id});
+  out.prim_info.push_back(int4{b.kind | b.flags | (shading_class(d, b.material) << PRIM_CLASS_SHIFT), b.material, b.xform, b.id});
 }
 
 bool texture_needs_uv(const RtbSceneDesc& d, int ti, int depth = 0) {
@@ -387,14 +401,14 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     for (const Baked& b : bl)
       for (int a = 0; a < 3; a++) M = std::max(M, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
   for (int a = 0; a < 3; a++) M = std::max(M, std::fabs(out.cam.center[a]));
-  const double pad = M * 6e-7;
+  const double pad = M * 1e-6;
 
   BvhBuilder bvh(B.surfaces);
   std::vector<int> node_remap;
   if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
   if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
   out.bvh_depth = bvh.max_depth;
-  for (int i : bvh.order) emit_prim(out, B.surfaces[i]);
+  for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
   out.n_surface_prims = (int)B.surfaces.size();
 
   // inner nodes get consecutive device indices in DFS order (root = 0)
@@ -444,7 +458,9 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     m.material = B.medium_material[mi];
     m.neg_inv_density = -1. / B.medium_density[mi];  // src/constant_medium.rs:26
     Box bx;
-    for (const Baked& b : B.boundaries[mi]) { emit_prim(out, b); bx.grow(b.lo, b.hi); }
+    for (const Baked& b : B.boundaries[mi]) { emit_prim(d, out, b); bx.grow(b.lo, b.hi); }
+    m.cls_fast = shading_class(d, m.material);
+    if (m.n_prims == 1 && B.boundaries[mi][0].kind == PRIM_SPHERE && !(B.boundaries[mi][0].flags & PRIM_FLAG_MOVING)) m.cls_fast |= 0x100;
     for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
     out.media.push_back(m);
   }

@@ -94,15 +94,6 @@ cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// wavefront pipeline -- implemented below (section "wavefront")
-// ------------------------------------------------------------------------------------------------
-size_t wavefront_workspace_bytes(const DScene&, int64_t) { return 0; }
-cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
-                                    bool collect_stats, void*, size_t, int64_t, cudaStream_t stream, int* launches) {
-  return launch_render_mega(S, s_begin, s_end, d_accum, d_stats, collect_stats, stream, launches);
-}
-
-// ------------------------------------------------------------------------------------------------
 // deterministic parity harness
 // ------------------------------------------------------------------------------------------------
 // Two kernels: (1) closest hit -> compact record {prim, t, alpha, beta}; (2) completion of the full

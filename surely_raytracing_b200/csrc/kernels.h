@@ -8,17 +8,22 @@
 
 namespace rtb {
 
-struct WavefrontBuffers;  // owned by the scene (api.cpp allocates through wavefront_alloc)
-
 // one persistent launch: per-lane path regeneration over [s_begin, s_end) for every pixel
 cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
                                bool collect_stats, cudaStream_t stream, int* launches);
 
 // wavefront pipeline: ray-gen / extend / shade+accumulate kernels over SoA ray queues
+struct WavefrontContext {   // per-scene host state of the wavefront driver
+  void* host_counters;      // pinned mirror of the device counters
+  int sms;
+  int extend_blocks_per_sm[2];
+};
+cudaError_t wavefront_context_create(WavefrontContext* ctx);
+void wavefront_context_destroy(WavefrontContext* ctx);
 size_t wavefront_workspace_bytes(const DScene& S, int64_t paths_per_wave);
-cudaError_t launch_render_wavefront(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
-                                    bool collect_stats, void* d_workspace, size_t workspace_bytes,
-                                    int64_t paths_per_wave, cudaStream_t stream, int* launches);
+cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx, int64_t s_begin, int64_t s_end,
+                                    float4* d_accum, DStats* d_stats, bool collect_stats, void* d_workspace,
+                                    size_t workspace_bytes, int64_t paths_per_wave, cudaStream_t stream, int* launches);
 
 size_t trace_scratch_bytes(int64_t n);
 cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits,

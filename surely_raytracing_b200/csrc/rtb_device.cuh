@@ -295,6 +295,28 @@ RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded 
 
 RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, double& t1, double& t2) {
   if (!medium_line_cull(m, r)) return false;
+  if (m.cls_fast & 0x100) {
+    // boundary = one static sphere: both probes of constant_medium.rs:46-55 evaluate the SAME two roots
+    // (Sphere::hit, object.rs:146-166), so compute them once -- bit-identical to two calls:
+    //   probe 1 over UNIVERSE returns root1 (when finite); probe 2 over (root1 + 1e-4, INF) rejects
+    //   root1 and returns root2 when it lies in the interval.
+    const double2* P = S.prims + (size_t)m.first_prim * PRIM_D2;
+    const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
+    const double ocx = dsub(r.ox, c01.x), ocy = dsub(r.oy, c01.y), ocz = dsub(r.oz, c2r.x);
+    const double a = ddot(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    const double half_b = ddot(ocx, ocy, ocz, r.dx, r.dy, r.dz);
+    const double c = dsub(ddot(ocx, ocy, ocz, ocx, ocy, ocz), dmul(c2r.y, c2r.y));
+    const double disc = dsub(dmul(half_b, half_b), dmul(a, c));
+    if (disc < 0.) return false;
+    const double sqrtd = sqrt(disc);
+    const double root1 = dsub(-half_b, sqrtd) / a, root2 = dsub(sqrtd, half_b) / a;
+    if (-RTB_INF < root1 && root1 < RTB_INF) {
+      t1 = root1;
+      t2 = root2;
+      return (t1 + 0.0001 < root2) && (root2 < RTB_INF);
+    }
+    // degenerate (zero direction ...): fall through to the generic probes
+  }
   t1 = boundary_probe(S, m, r, -RTB_INF);          // boundary.hit(r, UNIVERSE)        :46
   if (!(t1 < RTB_INF)) return false;
   t2 = boundary_probe(S, m, r, t1 + 0.0001);       // boundary.hit(r, (t1+1e-4, INF))  :49-55
@@ -558,6 +580,7 @@ struct Event {
   double a, b;
   int prim;   // >= 0 surface primitive (BVH order); -1 none
   int medium; // >= 0: the event is a scatter inside this medium
+  int have_ab;  // quad planar coordinates a, b are valid (else shade recomputes them when a texture needs uv)
 };
 
 // world.hit(r, Interval{0.0001, INF})  src/render.rs:264-270
@@ -566,7 +589,7 @@ RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st)
   Hit best;
   hit_reset(best);
   if (S.n_surface_prims > 0) closest_surface<STATS>(S, ps.ray, 0.0001, best, st);
-  ev.t = best.t; ev.a = best.a; ev.b = best.b; ev.prim = best.prim; ev.medium = -1;
+  ev.t = best.t; ev.a = best.a; ev.b = best.b; ev.prim = best.prim; ev.medium = -1; ev.have_ab = 1;
   if (S.n_media > 0) {
     Rand4 u;
     for (int mi = 0; mi < S.n_media; mi++) {
@@ -604,7 +627,15 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
       const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
       front = ddot(r.dx, r.dy, r.dz, n01.x, n01.y, n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
       n = v3((float)n01.x, (float)n01.y, (float)n2d.x);
-      tu = (float)ev.a; tv = (float)ev.b;
+      if (needs_uv) {
+        double ta = ev.a, tb = ev.b;
+        if (!ev.have_ab) {
+          ta = tb = 0.;  // wavefront hit records carry only (t, id): re-evaluate Quad::hit for alpha/beta
+          double tt;
+          quad_test(P, r, -RTB_INF, RTB_INF, tt, ta, tb);
+        }
+        tu = (float)ta; tv = (float)tb;
+      }
     } else {
       const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
       double cx = c01.x, cy = c01.y, cz = c2r.x;

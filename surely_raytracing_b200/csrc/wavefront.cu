@@ -1,0 +1,490 @@
+// wavefront.cu -- the wavefront pipeline of the hot path (the product pipeline; the megakernel in
+// kernels.cu is the A/B arm).
+//
+// One iteration advances every in-flight path by one segment:
+//
+//   k_wf_extend     closest surface hit: persistent warps with dynamic ray     HittableList::hit / BvhNode::hit
+//                   fetch and speculative while-while traversal                hittable.rs:88-109, 216-236
+//   k_wf_resolve    constant-medium events + shading class -> per-class bins   ConstantMedium::hit  constant_medium.rs:41-95
+//   k_wf_shade      emit / scatter / mixture-pdf sample, class-sorted;         ray_color  render.rs:271-297
+//                   survivors are appended (densely) to the next ray queue, finished paths accumulate
+//   k_wf_generate   tops the next queue up with new (pixel, stratum) rays      get_ray  render.rs:218-249
+//
+// Data layout in HBM (DESIGN.md "Queues"): two dense ray queues of 64-byte records (4 x 16 B: origin
+// f64x3 | direction f32x3, time | throughput f32x3, pixel | stratum, bounce) in QUEUE ORDER -- there
+// is no slot indirection, so extend and resolve stream them; one 16-byte hit record {t f64, id} per
+// queue position; per-class bins of queue positions for the shade stage.  All counters live on the
+// device; the host only polls "paths left" every few iterations.
+//
+// Why this shape (ncu, profiles/r01_*): the megakernel keeps only 9.6 of 32 lanes active because
+// BVH trip counts differ per ray and lanes sit in different phases; here every kernel is one phase,
+// extend refills idle lanes, and shading runs sorted by class.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "rtb_device.cuh"
+
+namespace rtb {
+
+struct WFCounters {
+  int n_in;           // rays in the current queue
+  int n_out;          // rays appended to the next queue (survivors, then regenerated paths)
+  int extend_cursor;  // dynamic-fetch cursor of k_wf_extend
+  int pad0;
+  int class_count[NUM_CLASSES];
+  unsigned long long next_path;    // camera paths started so far
+  unsigned long long total_paths;  // to start in this render call (padded tiles included)
+  unsigned long long segments;     // sum of n_in over iterations
+  unsigned long long pad1;
+};
+
+struct RayRec { uint4 a, b, c, d; };  // 64 B, see pack/unpack
+struct alignas(16) HitRec { double t; int id; int pad; };
+
+struct WFQueues {
+  RayRec* rays_a;
+  RayRec* rays_b;
+  HitRec* hits;
+  int* bins;  // NUM_CLASSES x capacity queue positions
+  WFCounters* c;
+  int capacity;
+};
+
+struct PathRec {  // unpacked RayRec
+  double ox, oy, oz;
+  float dx, dy, dz, time;
+  float bx, by, bz;
+  uint32_t pixel, sample, bounce;
+};
+
+__device__ __forceinline__ RayRec pack(const PathRec& p) {
+  RayRec r;
+  r.a.x = (unsigned)__double2loint(p.ox); r.a.y = (unsigned)__double2hiint(p.ox);
+  r.a.z = (unsigned)__double2loint(p.oy); r.a.w = (unsigned)__double2hiint(p.oy);
+  r.b.x = (unsigned)__double2loint(p.oz); r.b.y = (unsigned)__double2hiint(p.oz);
+  r.b.z = __float_as_uint(p.dx); r.b.w = __float_as_uint(p.dy);
+  r.c.x = __float_as_uint(p.dz); r.c.y = __float_as_uint(p.time);
+  r.c.z = __float_as_uint(p.bx); r.c.w = __float_as_uint(p.by);
+  r.d.x = __float_as_uint(p.bz); r.d.y = p.pixel; r.d.z = p.sample; r.d.w = p.bounce;
+  return r;
+}
+__device__ __forceinline__ void unpack_geom(const uint4& a, const uint4& b, const uint4& c, PathRec& p) {
+  p.ox = __hiloint2double((int)a.y, (int)a.x); p.oy = __hiloint2double((int)a.w, (int)a.z);
+  p.oz = __hiloint2double((int)b.y, (int)b.x);
+  p.dx = __uint_as_float(b.z); p.dy = __uint_as_float(b.w);
+  p.dz = __uint_as_float(c.x); p.time = __uint_as_float(c.y);
+  p.bx = __uint_as_float(c.z); p.by = __uint_as_float(c.w);
+}
+__device__ __forceinline__ void unpack_state(const uint4& d, PathRec& p) {
+  p.bz = __uint_as_float(d.x); p.pixel = d.y; p.sample = d.z; p.bounce = d.w;
+}
+__device__ __forceinline__ Ray to_ray(const PathRec& p) {
+  Ray r;
+  r.ox = p.ox; r.oy = p.oy; r.oz = p.oz;
+  r.dx = (double)p.dx; r.dy = (double)p.dy; r.dz = (double)p.dz; r.time = (double)p.time;
+  return r;
+}
+
+constexpr uint32_t PADDING_PIXEL = 0xFFFFFFFFu;  // inert lane of a border tile
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t wavefront_workspace_bytes(const DScene&, int64_t n) {
+  return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up((size_t)NUM_CLASSES * n * sizeof(int)) +
+         align_up(sizeof(WFCounters));
+}
+
+static WFQueues carve(void* ws, int64_t n) {
+  char* p = static_cast<char*>(ws);
+  auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
+  WFQueues q;
+  q.rays_a = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
+  q.rays_b = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
+  q.hits = reinterpret_cast<HitRec*>(take(n * sizeof(HitRec)));
+  q.bins = reinterpret_cast<int*>(take((size_t)NUM_CLASSES * n * sizeof(int)));
+  q.c = reinterpret_cast<WFCounters*>(take(sizeof(WFCounters)));
+  q.capacity = (int)n;
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bookkeeping (one thread)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_wf_init(WFQueues Q, unsigned long long total_paths) {
+  WFCounters z = {};
+  z.total_paths = total_paths;
+  *Q.c = z;
+}
+
+// after shade + generate: the out queue becomes the in queue of the next iteration
+__global__ void k_wf_advance(WFQueues Q) {
+  WFCounters* c = Q.c;
+  const unsigned long long left = c->total_paths - c->next_path;
+  const unsigned long long room = (unsigned long long)(Q.capacity - c->n_out);
+  const unsigned long long gen = left < room ? left : room;
+  c->next_path += gen;
+  c->n_in = c->n_out + (int)gen;
+  c->segments += (unsigned long long)c->n_in;
+  c->n_out = 0;
+  c->extend_cursor = 0;
+  for (int k = 0; k < NUM_CLASSES; k++) c->class_count[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generate: path id -> (stratum, pixel).  Ids enumerate 8x4 pixel tiles padded to 32 lanes, so the
+// 32 consecutive rays of one warp-fetch in extend are one coherent tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DScene S, WFQueues Q, long long s_begin,
+                                                      RayRec* __restrict__ out) {
+  const WFCounters* c = Q.c;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long left = c->total_paths - c->next_path;
+  const int n_out = c->n_out;
+  if (i >= Q.capacity - n_out || (unsigned long long)i >= left) return;
+  const unsigned long long pid = c->next_path + (unsigned long long)i;
+  const uint32_t tiles_x = (uint32_t)(S.cam.width + 7) >> 3;
+  const uint32_t tiles = tiles_x * (uint32_t)((S.cam.height + 3) >> 2);
+  const unsigned long long padded = (unsigned long long)tiles * 32ull;
+  const uint32_t sample = (uint32_t)(s_begin + (long long)(pid / padded));
+  const uint32_t idx = (uint32_t)(pid % padded), tile = idx >> 5, lane = idx & 31u;
+  const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u), y = (tile / tiles_x) * 4u + (lane >> 3);
+  PathRec p;
+  if (x < (uint32_t)S.cam.width && y < (uint32_t)S.cam.height) {
+    const uint32_t pixel = y * (uint32_t)S.cam.width + x;
+    PathState ps;
+    generate_primary(S, pixel, sample, ps);
+    p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
+    p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz; p.time = (float)ps.ray.time;
+    p.bx = p.by = p.bz = 1.f;
+    p.pixel = pixel;
+  } else {  // padding lane: dies in its first shade without touching the image
+    p.ox = p.oy = p.oz = 0.;
+    p.dx = p.dy = 0.f; p.dz = 1.f; p.time = 0.f;
+    p.bx = p.by = p.bz = 0.f;
+    p.pixel = PADDING_PIXEL;
+  }
+  p.sample = sample;
+  p.bounce = 0u;
+  out[n_out + i] = pack(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// extend: persistent warps, dynamic fetch, speculative while-while traversal (Aila & Laine 2009):
+// a lane that reaches a leaf postpones it and keeps descending until every lane of the warp holds a
+// leaf or has run out of nodes; then the leaves are tested together.  fp32 conservative slabs in
+// fused form (t = plane * inv_d - o * inv_d), f64 reference-order primitive tests.
+// ------------------------------------------------------------------------------------------------
+constexpr int WF_EXTEND_BLOCK = 128;
+constexpr int WF_FETCH_THRESHOLD = 20;  // refill when fewer than this many lanes hold a ray
+constexpr int TRAV_DONE = 0x7FFFFFFF;
+
+template <bool STATS>
+__global__ void __launch_bounds__(WF_EXTEND_BLOCK) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
+                                                               const RayRec* __restrict__ rays_in,
+                                                               DStats* __restrict__ stats) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int n = Q.c->n_in;
+  unsigned long long st_nodes = 0, st_prims = 0;
+  bool have = false, exhausted = false;
+  int pos = -1;
+  Ray r;
+  float idx = 0.f, idy = 0.f, idz = 0.f, oxi = 0.f, oyi = 0.f, ozi = 0.f, tbest32 = 0.f;
+  const float tmin32 = __double2float_rd(0.0001);
+  Hit best;
+  hit_reset(best);
+  int stack[BVH_STACK];
+  int sp = 0, node = TRAV_DONE, leaf = 0;  // leaf: postponed leaf reference (< 0) or 0
+  const bool any_surface = S.n_surface_prims > 0;
+  for (;;) {
+    // ---- dynamic fetch -------------------------------------------------------------------------
+    const unsigned have_mask = __ballot_sync(FULL, have);
+    if (__popc(have_mask) < WF_FETCH_THRESHOLD) {
+      const unsigned need = __ballot_sync(FULL, !have && !exhausted);
+      if (need) {
+        int base = 0;
+        const int leader = __ffs(need) - 1;
+        if (lane == leader) base = atomicAdd(&Q.c->extend_cursor, __popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!have && !exhausted) {
+          const int k = base + __popc(need & ((1u << lane) - 1u));
+          if (k < n) {
+            pos = k;
+            const uint4* R = reinterpret_cast<const uint4*>(rays_in + k);
+            const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+            PathRec p;
+            unpack_geom(a, b, c, p);
+            r = to_ray(p);
+            idx = 1.0f / p.dx; idy = 1.0f / p.dy; idz = 1.0f / p.dz;
+            oxi = (float)r.ox * idx; oyi = (float)r.oy * idy; ozi = (float)r.oz * idz;
+            hit_reset(best);
+            tbest32 = __double2float_ru(best.t);
+            sp = 0;
+            leaf = 0;
+            node = any_surface ? 0 : TRAV_DONE;
+            have = true;
+          } else {
+            exhausted = true;
+          }
+        }
+      }
+    }
+    if (!__any_sync(FULL, have)) break;
+    // ---- inner nodes, speculative: keep descending after the first leaf is found -------------------
+    while (node >= 0 && node != TRAV_DONE) {
+      if (STATS) st_nodes++;
+      const float4* N = S.nodes + 4 * (size_t)node;
+      const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+      float a0 = fmaf(n0.x, idx, -oxi), a1 = fmaf(n0.y, idx, -oxi);
+      float b0 = fmaf(n0.z, idy, -oyi), b1 = fmaf(n0.w, idy, -oyi);
+      float c0 = fmaf(n2.x, idz, -ozi), c1 = fmaf(n2.y, idz, -ozi);
+      const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+      const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+      a0 = fmaf(n1.x, idx, -oxi); a1 = fmaf(n1.y, idx, -oxi);
+      b0 = fmaf(n1.z, idy, -oyi); b1 = fmaf(n1.w, idy, -oyi);
+      c0 = fmaf(n2.z, idz, -ozi); c1 = fmaf(n2.w, idz, -ozi);
+      const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+      const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+      const bool h0 = tn0 <= fmaf(fabsf(tf0), 4e-6f, tf0);
+      const bool h1 = tn1 <= fmaf(fabsf(tf1), 4e-6f, tf1);
+      int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
+        stack[sp++] = ch1;
+        node = ch0;
+      } else if (h0) {
+        node = ch0;
+      } else if (h1) {
+        node = ch1;
+      } else {
+        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+      }
+      if (node < 0 && leaf == 0) {  // first leaf: postpone it and continue with the next node
+        leaf = node;
+        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+      }
+      // every lane still in this loop holds a leaf already: stop speculating and test the leaves
+      if (!__any_sync(__activemask(), leaf == 0)) break;
+    }
+    // ---- leaves: the postponed one, then the current node if it is a leaf too -------------------------
+    while (leaf < 0) {
+      const int l = ~leaf;
+      const int first = l >> 3, count = (l & 7) + 1;
+      for (int i = 0; i < count; i++) {
+        if (STATS) st_prims++;
+        test_prim(S, first + i, r, 0.0001, best);
+      }
+      leaf = 0;
+      if (node < 0) {
+        leaf = node;
+        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+      }
+    }
+    if (have) tbest32 = __double2float_ru(best.t);
+    if (have && node == TRAV_DONE) {
+      HitRec h;
+      h.t = best.t; h.id = best.prim; h.pad = 0;
+      Q.hits[pos] = h;
+      have = false;
+    }
+  }
+  if (STATS) {
+    atomicAdd(&stats->node_visits, st_nodes);
+    atomicAdd(&stats->prim_tests, st_prims);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve: medium events against the closest surface, then shading class -> bins of queue positions
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ DScene S, WFQueues Q,
+                                                    const RayRec* __restrict__ rays_in, DStats* __restrict__ stats) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int n = Q.c->n_in;
+  int cls = -1;
+  if (i < n) {
+    HitRec h = Q.hits[i];
+    if (S.n_media > 0) {
+      const uint4* R = reinterpret_cast<const uint4*>(rays_in + i);
+      const uint4 d = __ldg(R + 3);
+      if (d.y != PADDING_PIXEL) {
+        const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+        PathRec p;
+        unpack_geom(a, b, c, p);
+        unpack_state(d, p);
+        const Ray r = to_ray(p);
+        Rand4 u;
+        bool changed = false;
+        for (int mi = 0; mi < S.n_media; mi++) {
+          if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
+          const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
+          const double tm = medium_event(S, mi, r, 0.0001, h.t, U);
+          if (tm < h.t) { h.t = tm; h.id = -2 - mi; changed = true; }
+        }
+        if (changed) Q.hits[i] = h;
+      }
+    }
+    cls = h.id == -1 ? CLS_MISS
+                     : (h.id >= 0 ? ((__ldg(S.prim_info + h.id).x >> PRIM_CLASS_SHIFT) & 0xF) : (S.media[-2 - h.id].cls_fast & 0xF));
+  }
+  // warp-aggregated append to the class bins
+  for (int k = 0; k < NUM_CLASSES; k++) {
+    const unsigned m = __ballot_sync(FULL, cls == k);
+    if (m == 0) continue;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&Q.c->class_count[k], __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (cls == k) Q.bins[(size_t)k * Q.capacity + base + __popc(m & ((1u << lane) - 1u))] = i;
+  }
+  if (STATS && i < n && S.n_media > 0 && lane == 0)
+    atomicAdd(&stats->medium_probes, (unsigned long long)S.n_media * (unsigned long long)min(32, n - i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade: class-sorted; survivors -> dense append to the next queue, finished -> accumulate
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
+                                                  const RayRec* __restrict__ rays_in, RayRec* __restrict__ rays_out,
+                                                  float4* __restrict__ accum, DStats* __restrict__ stats) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const WFCounters* c = Q.c;
+  int cls = -1, pos = i;  // locate (class, index): prefix over 8 counters
+#pragma unroll
+  for (int k = 0; k < NUM_CLASSES; k++) {
+    const int cnt = c->class_count[k];
+    if (cls < 0) {
+      if (pos < cnt) cls = k; else pos -= cnt;
+    }
+  }
+  bool alive = false;
+  RayRec out;
+  DStats st = {0, 0, 0, 0, 0, 0};
+  if (cls >= 0) {
+    const int q = Q.bins[(size_t)cls * Q.capacity + pos];
+    const uint4* R = reinterpret_cast<const uint4*>(rays_in + q);
+    const uint4 d = __ldg(R + 3);
+    if (d.y != PADDING_PIXEL) {
+      const uint4 a = __ldg(R + 0), b = __ldg(R + 1), cc = __ldg(R + 2);
+      const HitRec h = Q.hits[q];
+      PathRec p;
+      unpack_geom(a, b, cc, p);
+      unpack_state(d, p);
+      PathState ps;
+      ps.ray = to_ray(p);
+      ps.bx = p.bx; ps.by = p.by; ps.bz = p.bz;
+      ps.pixel = p.pixel; ps.sample = p.sample; ps.bounce = p.bounce;
+      Event ev;
+      ev.t = h.t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
+      ev.prim = h.id >= 0 ? h.id : -1;
+      ev.medium = h.id <= -2 ? -2 - h.id : -1;
+      float Lr = 0.f, Lg = 0.f, Lb = 0.f;
+      alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);
+      if (alive) {
+        p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
+        p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
+        p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
+        p.bounce = ps.bounce;
+        out = pack(p);
+      } else {
+        const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
+        float* acc = reinterpret_cast<float*>(accum + p.pixel);
+        if (finite || (S.flags & 2u)) {
+          if (Lr != 0.f) atomicAdd(acc + 0, Lr);
+          if (Lg != 0.f) atomicAdd(acc + 1, Lg);
+          if (Lb != 0.f) atomicAdd(acc + 2, Lb);
+        } else if (STATS) {
+          st.nonfinite++;
+        }
+        atomicAdd(acc + 3, 1.0f);
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, alive);
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&Q.c->n_out, __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (alive) rays_out[base + __popc(m & ((1u << lane) - 1u))] = out;
+  }
+  if (STATS && st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+cudaError_t wavefront_context_create(WavefrontContext* ctx) {
+  ctx->host_counters = nullptr;
+  cudaError_t e = cudaMallocHost(&ctx->host_counters, sizeof(WFCounters));
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ctx->sms = 148;
+  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, dev);
+  ctx->extend_blocks_per_sm[0] = ctx->extend_blocks_per_sm[1] = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[0], k_wf_extend<false>, WF_EXTEND_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[1], k_wf_extend<true>, WF_EXTEND_BLOCK, 0);
+  return cudaGetLastError();
+}
+
+void wavefront_context_destroy(WavefrontContext* ctx) {
+  if (ctx->host_counters) cudaFreeHost(ctx->host_counters);
+  ctx->host_counters = nullptr;
+}
+
+cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx, int64_t s_begin, int64_t s_end,
+                                    float4* d_accum, DStats* d_stats, bool collect_stats, void* d_workspace,
+                                    size_t workspace_bytes, int64_t capacity, cudaStream_t stream, int* launches) {
+  if (workspace_bytes < wavefront_workspace_bytes(S, capacity)) return cudaErrorInvalidValue;
+  WFQueues Q = carve(d_workspace, capacity);
+  const unsigned long long tiles = (unsigned long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
+  const unsigned long long total = tiles * 32ull * (unsigned long long)(s_end - s_begin);
+  const int per_sm = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
+  const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
+  const unsigned blocks256 = (unsigned)((capacity + 255) / 256), blocks128 = (unsigned)((capacity + 127) / 128);
+  int n_launch = 0;
+  k_wf_init<<<1, 1, 0, stream>>>(Q, total);
+  n_launch++;
+  RayRec* in = Q.rays_a;
+  RayRec* out = Q.rays_b;
+  WFCounters* h_c = static_cast<WFCounters*>(ctx.host_counters);  // pinned mirror for the (sparse) host polls
+  cudaError_t e = cudaSuccess;
+  // Iterations needed if every path lived exactly one segment: a lower bound; after that, poll.
+  const int poll_every = 8;
+  for (long long iter = 0;; iter++) {
+    // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue
+    k_wf_generate<<<blocks256, 256, 0, stream>>>(S, Q, (long long)s_begin, out);
+    k_wf_advance<<<1, 1, 0, stream>>>(Q);
+    { RayRec* t = in; in = out; out = t; }
+    if (collect_stats) {
+      k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
+      k_wf_resolve<true><<<blocks256, 256, 0, stream>>>(S, Q, in, d_stats);
+      k_wf_shade<true><<<blocks128, 128, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
+    } else {
+      k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
+      k_wf_resolve<false><<<blocks256, 256, 0, stream>>>(S, Q, in, d_stats);
+      k_wf_shade<false><<<blocks128, 128, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
+    }
+    n_launch += 5;
+    if ((iter % poll_every) == poll_every - 1) {
+      e = cudaMemcpyAsync(h_c, Q.c, sizeof(WFCounters), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) return e;
+      if (h_c->next_path >= h_c->total_paths && h_c->n_out == 0) break;
+    }
+  }
+  if (collect_stats)
+    e = cudaMemcpyAsync(&d_stats->segments, &Q.c->segments, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
+  if (launches) *launches += n_launch;
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+}  // namespace rtb
