@@ -70,6 +70,8 @@ struct DMedium {
   int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere
   double neg_inv_density;
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
+  float diag;               // diagonal of that box: no chord of the boundary is longer
+  float pad;
 };
 
 struct alignas(16) DLight {

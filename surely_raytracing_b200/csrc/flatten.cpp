@@ -462,6 +462,10 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     m.cls_fast = shading_class(d, m.material);
     if (m.n_prims == 1 && B.boundaries[mi][0].kind == PRIM_SPHERE && !(B.boundaries[mi][0].flags & PRIM_FLAG_MOVING)) m.cls_fast |= 0x100;
     for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
+    {
+      const double ex = (double)m.hi[0] - m.lo[0], ey = (double)m.hi[1] - m.lo[1], ez = (double)m.hi[2] - m.lo[2];
+      m.diag = round_up(std::sqrt(ex * ex + ey * ey + ez * ez) * (1. + 1e-6));
+    }
     out.media.push_back(m);
   }
   return RTB_OK;

@@ -326,15 +326,31 @@ RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, do
 // returns the event parameter t (or +inf) for medium `mi`, given the closest surface so far
 RTB_DEV double medium_event(const DScene& S, int mi, const Ray& r, double tmin, double tmax, float U) {
   const DMedium& m = S.media[mi];
+  const float log_u = logf(U);  // U = 0 -> -inf -> hit_distance +inf: no event
+  {  // the shortcut below, first in fp32 with a wide margin (most rays leave here)
+    const float len32 = sqrtf((float)r.dx * (float)r.dx + (float)r.dy * (float)r.dy + (float)r.dz * (float)r.dz);
+    const float span32 = ((float)tmax - (float)tmin) * len32;
+    const float hd32 = (float)m.neg_inv_density * log_u;
+    if (hd32 > fminf(span32, m.diag) * 1.0001f + 1e-6f) return RTB_INF;
+  }
+  const double ray_length = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+  const double hit_distance = m.neg_inv_density * (double)log_u;
+  // Exact shortcut: the event needs hit_distance <= (t2' - t1') * |d|, and that product can exceed
+  // neither the clamped ray span (tmax - tmin) * |d| nor the longest chord of the boundary (its box
+  // diagonal).  A free flight beyond both (with slack for rounding) cannot scatter: skip the two
+  // boundary probes.  For the thin book-2 fog (1/rho = 1e4) this removes ~9 of 10 probes.
+  {
+    const double span = (tmax - tmin) * ray_length;
+    const double bound = fmin(span, (double)m.diag);
+    if (hit_distance > bound * (1. + 1e-9) + 1e-12) return RTB_INF;
+  }
   double t1, t2;
   if (!medium_interval(S, m, r, t1, t2)) return RTB_INF;
   if (t1 < tmin) t1 = tmin;   // :58-60
   if (t2 > tmax) t2 = tmax;   // :61-63
   if (t1 >= t2) return RTB_INF;
   if (t1 < 0.) t1 = 0.;       // :69-71
-  const double ray_length = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
   const double distance_inside_boundary = (t2 - t1) * ray_length;
-  const double hit_distance = m.neg_inv_density * (double)logf(U);  // U = 0 -> +inf: no event
   if (hit_distance > distance_inside_boundary) return RTB_INF;
   return t1 + hit_distance / ray_length;
 }

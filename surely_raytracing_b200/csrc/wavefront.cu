@@ -21,6 +21,9 @@
 // extend refills idle lanes, and shading runs sorted by class.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.h"
 #include "rtb_device.cuh"
 
@@ -31,7 +34,6 @@ struct WFCounters {
   int n_out;          // rays appended to the next queue (survivors, then regenerated paths)
   int extend_cursor;  // dynamic-fetch cursor of k_wf_extend
   int pad0;
-  int class_count[NUM_CLASSES];
   unsigned long long next_path;    // camera paths started so far
   unsigned long long total_paths;  // to start in this render call (padded tiles included)
   unsigned long long segments;     // sum of n_in over iterations
@@ -45,7 +47,6 @@ struct WFQueues {
   RayRec* rays_a;
   RayRec* rays_b;
   HitRec* hits;
-  int* bins;  // NUM_CLASSES x capacity queue positions
   WFCounters* c;
   int capacity;
 };
@@ -90,8 +91,7 @@ constexpr uint32_t PADDING_PIXEL = 0xFFFFFFFFu;  // inert lane of a border tile
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t wavefront_workspace_bytes(const DScene&, int64_t n) {
-  return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up((size_t)NUM_CLASSES * n * sizeof(int)) +
-         align_up(sizeof(WFCounters));
+  return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up(sizeof(WFCounters));
 }
 
 static WFQueues carve(void* ws, int64_t n) {
@@ -101,7 +101,6 @@ static WFQueues carve(void* ws, int64_t n) {
   q.rays_a = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
   q.rays_b = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
   q.hits = reinterpret_cast<HitRec*>(take(n * sizeof(HitRec)));
-  q.bins = reinterpret_cast<int*>(take((size_t)NUM_CLASSES * n * sizeof(int)));
   q.c = reinterpret_cast<WFCounters*>(take(sizeof(WFCounters)));
   q.capacity = (int)n;
   return q;
@@ -127,7 +126,6 @@ __global__ void k_wf_advance(WFQueues Q) {
   c->segments += (unsigned long long)c->n_in;
   c->n_out = 0;
   c->extend_cursor = 0;
-  for (int k = 0; k < NUM_CLASSES; k++) c->class_count[k] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // fused form (t = plane * inv_d - o * inv_d), f64 reference-order primitive tests.
 // ------------------------------------------------------------------------------------------------
 constexpr int WF_EXTEND_BLOCK = 128;
-constexpr int WF_FETCH_THRESHOLD = 20;  // refill when fewer than this many lanes hold a ray
+constexpr int WF_FETCH_THRESHOLD = 28;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
 
 template <bool STATS>
@@ -295,95 +293,108 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK) k_wf_extend(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// resolve: medium events against the closest surface, then shading class -> bins of queue positions
+// shade (fused resolve + sort + shade).  One block owns WF_SHADE_BLOCK consecutive queue positions:
+//   1. stream the ray + hit records in (coalesced), add the constant-medium events
+//      (ConstantMedium::hit, constant_medium.rs:41-95) and look up the shading class;
+//   2. block-local counting sort by class through shared memory, so that a warp shades one class
+//      (the Perlin texture costs ~1k instructions, a solid Lambertian ~150: they must not share a warp);
+//   3. shade (ray_color's match arms, render.rs:271-297); survivors are appended densely to the next
+//      queue with one atomic per block, finished paths add their radiance to the image.
+// No global bins, no gathers: every global access of this kernel is sequential.
 // ------------------------------------------------------------------------------------------------
+constexpr int WF_SHADE_BLOCK = 256;
+constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
+
+struct ShadeItem {  // what moves through shared memory to the lane that shades it (80 B)
+  uint4 a, b, c, d;
+  double t;
+  int id;
+  int cls;
+};
+
 template <bool STATS>
-__global__ void __launch_bounds__(256) k_wf_resolve(const __grid_constant__ DScene S, WFQueues Q,
-                                                    const RayRec* __restrict__ rays_in, DStats* __restrict__ stats) {
+__global__ void __launch_bounds__(WF_SHADE_BLOCK, 3) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
+                                                            const RayRec* __restrict__ rays_in,
+                                                            RayRec* __restrict__ rays_out, float4* __restrict__ accum,
+                                                            DStats* __restrict__ stats) {
   const unsigned FULL = 0xFFFFFFFFu;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  __shared__ ShadeItem items[WF_SHADE_BLOCK];
+  __shared__ int warp_count[NUM_CLASSES][WF_SHADE_WARPS];  // [cls][warp]
+  __shared__ int class_base[NUM_CLASSES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * WF_SHADE_BLOCK + tid;
   const int n = Q.c->n_in;
-  int cls = -1;
+  if (blockIdx.x * WF_SHADE_BLOCK >= n) return;  // whole block idle (uniform)
+  // ---- 1. load + medium events + class -----------------------------------------------------------
+  ShadeItem it;
+  it.cls = -1;
   if (i < n) {
-    HitRec h = Q.hits[i];
-    if (S.n_media > 0) {
-      const uint4* R = reinterpret_cast<const uint4*>(rays_in + i);
-      const uint4 d = __ldg(R + 3);
-      if (d.y != PADDING_PIXEL) {
-        const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+    const uint4* R = reinterpret_cast<const uint4*>(rays_in + i);
+    it.a = __ldg(R + 0); it.b = __ldg(R + 1); it.c = __ldg(R + 2); it.d = __ldg(R + 3);
+    const HitRec h = Q.hits[i];
+    it.t = h.t; it.id = h.id;
+    if (it.d.y == PADDING_PIXEL) {
+      it.cls = CLS_MISS;
+    } else {
+      if (S.n_media > 0) {
         PathRec p;
-        unpack_geom(a, b, c, p);
-        unpack_state(d, p);
+        unpack_geom(it.a, it.b, it.c, p);
+        unpack_state(it.d, p);
         const Ray r = to_ray(p);
         Rand4 u;
-        bool changed = false;
         for (int mi = 0; mi < S.n_media; mi++) {
           if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
           const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-          const double tm = medium_event(S, mi, r, 0.0001, h.t, U);
-          if (tm < h.t) { h.t = tm; h.id = -2 - mi; changed = true; }
+          const double tm = medium_event(S, mi, r, 0.0001, it.t, U);
+          if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
         }
-        if (changed) Q.hits[i] = h;
       }
+      it.cls = it.id == -1 ? CLS_MISS
+                           : (it.id >= 0 ? ((__ldg(S.prim_info + it.id).x >> PRIM_CLASS_SHIFT) & 0xF)
+                                         : (S.media[-2 - it.id].cls_fast & 0xF));
     }
-    cls = h.id == -1 ? CLS_MISS
-                     : (h.id >= 0 ? ((__ldg(S.prim_info + h.id).x >> PRIM_CLASS_SHIFT) & 0xF) : (S.media[-2 - h.id].cls_fast & 0xF));
   }
-  // warp-aggregated append to the class bins
-  for (int k = 0; k < NUM_CLASSES; k++) {
-    const unsigned m = __ballot_sync(FULL, cls == k);
-    if (m == 0) continue;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&Q.c->class_count[k], __popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (cls == k) Q.bins[(size_t)k * Q.capacity + base + __popc(m & ((1u << lane) - 1u))] = i;
-  }
-  if (STATS && i < n && S.n_media > 0 && lane == 0)
-    atomicAdd(&stats->medium_probes, (unsigned long long)S.n_media * (unsigned long long)min(32, n - i));
-}
-
-// ------------------------------------------------------------------------------------------------
-// shade: class-sorted; survivors -> dense append to the next queue, finished -> accumulate
-// ------------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
-                                                  const RayRec* __restrict__ rays_in, RayRec* __restrict__ rays_out,
-                                                  float4* __restrict__ accum, DStats* __restrict__ stats) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const WFCounters* c = Q.c;
-  int cls = -1, pos = i;  // locate (class, index): prefix over 8 counters
+  // ---- 2. block-local counting sort by class -------------------------------------------------------
+  int rank_in_warp = 0;
 #pragma unroll
   for (int k = 0; k < NUM_CLASSES; k++) {
-    const int cnt = c->class_count[k];
-    if (cls < 0) {
-      if (pos < cnt) cls = k; else pos -= cnt;
-    }
+    const unsigned m = __ballot_sync(FULL, it.cls == k);
+    if (lane == 0) warp_count[k][warp] = __popc(m);
+    if (it.cls == k) rank_in_warp = __popc(m & ((1u << lane) - 1u));
   }
+  __syncthreads();
+  if (tid < NUM_CLASSES) {  // exclusive prefix over classes (8 x 8 counters: one thread per class is enough)
+    int total_before = 0;
+    for (int k = 0; k < tid; k++)
+      for (int w = 0; w < WF_SHADE_WARPS; w++) total_before += warp_count[k][w];
+    class_base[tid] = total_before;
+  }
+  __syncthreads();
+  if (it.cls >= 0) {
+    int dst = class_base[it.cls] + rank_in_warp;
+    for (int w = 0; w < warp; w++) dst += warp_count[it.cls][w];
+    items[dst] = it;
+  }
+  __syncthreads();
+  const int n_block = min(WF_SHADE_BLOCK, n - blockIdx.x * WF_SHADE_BLOCK);
+  // ---- 3. shade the item at sorted position `tid` -----------------------------------------------------
   bool alive = false;
   RayRec out;
   DStats st = {0, 0, 0, 0, 0, 0};
-  if (cls >= 0) {
-    const int q = Q.bins[(size_t)cls * Q.capacity + pos];
-    const uint4* R = reinterpret_cast<const uint4*>(rays_in + q);
-    const uint4 d = __ldg(R + 3);
-    if (d.y != PADDING_PIXEL) {
-      const uint4 a = __ldg(R + 0), b = __ldg(R + 1), cc = __ldg(R + 2);
-      const HitRec h = Q.hits[q];
+  if (tid < n_block) {
+    const ShadeItem me = items[tid];
+    if (me.d.y != PADDING_PIXEL) {
       PathRec p;
-      unpack_geom(a, b, cc, p);
-      unpack_state(d, p);
+      unpack_geom(me.a, me.b, me.c, p);
+      unpack_state(me.d, p);
       PathState ps;
       ps.ray = to_ray(p);
       ps.bx = p.bx; ps.by = p.by; ps.bz = p.bz;
       ps.pixel = p.pixel; ps.sample = p.sample; ps.bounce = p.bounce;
       Event ev;
-      ev.t = h.t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
-      ev.prim = h.id >= 0 ? h.id : -1;
-      ev.medium = h.id <= -2 ? -2 - h.id : -1;
+      ev.t = me.t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
+      ev.prim = me.id >= 0 ? me.id : -1;
+      ev.medium = me.id <= -2 ? -2 - me.id : -1;
       float Lr = 0.f, Lg = 0.f, Lb = 0.f;
       alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);
       if (alive) {
@@ -406,6 +417,8 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
       }
     }
   }
+  // ---- survivors: one atomic per warp, dense coalesced append.  (A per-block aggregate would need a
+  //      barrier after shading, and ncu showed every warp then waits for the block's slowest class.)
   const unsigned m = __ballot_sync(FULL, alive);
   if (m) {
     const int leader = __ffs(m) - 1;
@@ -414,7 +427,10 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DScene
     base = __shfl_sync(FULL, base, leader);
     if (alive) rays_out[base + __popc(m & ((1u << lane) - 1u))] = out;
   }
-  if (STATS && st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
+  if (STATS) {
+    if (st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
+    if (tid == 0 && S.n_media > 0) atomicAdd(&stats->medium_probes, (unsigned long long)S.n_media * (unsigned long long)n_block);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,7 +464,8 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   const unsigned long long total = tiles * 32ull * (unsigned long long)(s_end - s_begin);
   const int per_sm = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
   const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
-  const unsigned blocks256 = (unsigned)((capacity + 255) / 256), blocks128 = (unsigned)((capacity + 127) / 128);
+  const unsigned blocks256 = (unsigned)((capacity + 255) / 256);
+  const unsigned shade_blocks = (unsigned)((capacity + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
   int n_launch = 0;
   k_wf_init<<<1, 1, 0, stream>>>(Q, total);
   n_launch++;
@@ -456,29 +473,46 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   RayRec* out = Q.rays_b;
   WFCounters* h_c = static_cast<WFCounters*>(ctx.host_counters);  // pinned mirror for the (sparse) host polls
   cudaError_t e = cudaSuccess;
-  // Iterations needed if every path lived exactly one segment: a lower bound; after that, poll.
-  const int poll_every = 8;
+  // RTB_WF_PROFILE=1: per-stage CUDA-event totals on stderr (analysis runs only; adds event overhead)
+  static const bool profile = getenv("RTB_WF_PROFILE") != nullptr;
+  cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double stage_ms[4] = {0., 0., 0., 0.};
+  if (profile)
+    for (auto& ev : pe) cudaEventCreate(&ev);
+  const int poll_every = profile ? 1 : 8;
   for (long long iter = 0;; iter++) {
     // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue
+    if (profile) cudaEventRecord(pe[0], stream);
     k_wf_generate<<<blocks256, 256, 0, stream>>>(S, Q, (long long)s_begin, out);
     k_wf_advance<<<1, 1, 0, stream>>>(Q);
+    if (profile) cudaEventRecord(pe[1], stream);
     { RayRec* t = in; in = out; out = t; }
     if (collect_stats) {
       k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
-      k_wf_resolve<true><<<blocks256, 256, 0, stream>>>(S, Q, in, d_stats);
-      k_wf_shade<true><<<blocks128, 128, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
+      if (profile) { cudaEventRecord(pe[2], stream); cudaEventRecord(pe[3], stream); }
+      k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
     } else {
       k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
-      k_wf_resolve<false><<<blocks256, 256, 0, stream>>>(S, Q, in, d_stats);
-      k_wf_shade<false><<<blocks128, 128, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
+      if (profile) { cudaEventRecord(pe[2], stream); cudaEventRecord(pe[3], stream); }
+      k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
     }
-    n_launch += 5;
+    if (profile) {
+      cudaEventRecord(pe[4], stream);
+      cudaEventSynchronize(pe[4]);
+      for (int k = 0; k < 4; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[k], pe[k + 1]); stage_ms[k] += ms; }
+    }
+    n_launch += 4;
     if ((iter % poll_every) == poll_every - 1) {
       e = cudaMemcpyAsync(h_c, Q.c, sizeof(WFCounters), cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
       if (e != cudaSuccess) return e;
       if (h_c->next_path >= h_c->total_paths && h_c->n_out == 0) break;
     }
+  }
+  if (profile) {
+    fprintf(stderr, "[rtb wavefront] iterations %d  segments %llu  generate %.2f ms  extend %.2f ms  resolve %.2f ms  shade %.2f ms\n",
+            (n_launch - 1) / 4, (unsigned long long)h_c->segments, stage_ms[0], stage_ms[1], stage_ms[2], stage_ms[3]);
+    for (auto& ev : pe) cudaEventDestroy(ev);
   }
   if (collect_stats)
     e = cudaMemcpyAsync(&d_stats->segments, &Q.c->segments, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
