@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,53 @@ cudaError_t upload(const std::vector<T>& v, const T** d_ptr, std::vector<void*>&
   return cudaSuccess;
 }
 
+// Process-wide cache of the large buffers (wavefront workspace, pinned download staging), keyed by
+// device: render_par-style callers create and destroy a scene per image, and re-allocating ~0.7 GB
+// for each call would dominate short renders.  Freed at process exit.
+struct BigBufferCache {
+  std::mutex mu;
+  struct Entry { int device; void* p; size_t bytes; bool pinned; bool in_use; };
+  std::vector<Entry> entries;
+  void* acquire(int device, size_t bytes, bool pinned, size_t* got, cudaError_t* err) {
+    std::lock_guard<std::mutex> lk(mu);
+    *err = cudaSuccess;
+    for (Entry& e : entries)
+      if (!e.in_use && e.device == device && e.pinned == pinned && e.bytes >= bytes) { e.in_use = true; *got = e.bytes; return e.p; }
+    for (size_t i = 0; i < entries.size(); i++)  // drop an idle, too-small buffer of the same kind
+      if (!entries[i].in_use && entries[i].device == device && entries[i].pinned == pinned) {
+        if (pinned) cudaFreeHost(entries[i].p); else cudaFree(entries[i].p);
+        entries.erase(entries.begin() + i);
+        break;
+      }
+    void* p = nullptr;
+    *err = pinned ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
+    if (*err != cudaSuccess) return nullptr;
+    entries.push_back(Entry{device, p, bytes, pinned, true});
+    *got = bytes;
+    return p;
+  }
+  void release(void* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (Entry& e : entries)
+      if (e.p == p) e.in_use = false;
+  }
+};
+BigBufferCache& big_cache() { static BigBufferCache c; return c; }
+
+struct CachedBuffer {  // a lease on a BigBufferCache entry
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(int device, size_t n, bool pinned) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) big_cache().release(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e;
+    p = big_cache().acquire(device, n, pinned, &bytes, &e);
+    return e;
+  }
+  ~CachedBuffer() { if (p) big_cache().release(p); }
+};
+
 struct DeviceBuffer {
   void* p = nullptr;
   size_t bytes = 0;
@@ -75,7 +123,8 @@ struct rtb_scene {
   DeviceBuffer scratch_a;  // harness inputs
   DeviceBuffer scratch_b;  // harness outputs
   DeviceBuffer scratch_c;
-  DeviceBuffer workspace;  // wavefront queues
+  CachedBuffer workspace;  // wavefront queues (leased from the process-wide cache)
+  CachedBuffer staging;    // pinned host staging of the accumulation buffer
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   WavefrontContext wf{};
   bool wf_ready = false;
@@ -209,7 +258,7 @@ static int render_into(rtb_scene* s, const RtbRenderParams* p, float4* d_accum, 
     if (p->pipeline != RTB_PIPELINE_MEGAKERNEL) {  // default = wavefront
       const int64_t cap = wavefront_capacity();
       const size_t ws = wavefront_workspace_bytes(s->dev, cap);
-      CU(s->workspace.reserve(ws));
+      CU(s->workspace.reserve(s->device, ws, false));
       if (!s->wf_ready) {
         CU(wavefront_context_create(&s->wf));
         s->wf_ready = true;
@@ -266,8 +315,10 @@ int rtb_render(rtb_scene* s, const RtbRenderParams* p, double* pixels_rgb, RtbSt
   CU(cudaMemsetAsync(s->accum.p, 0, n * sizeof(float4), 0));
   rc = render_into(s, p, static_cast<float4*>(s->accum.p), 0);
   if (rc != RTB_OK) return rc;
-  std::vector<float4> h(n);
-  CU(cudaMemcpy(h.data(), s->accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  CU(s->staging.reserve(s->device, n * sizeof(float4), true));
+  const float4* h = static_cast<const float4*>(s->staging.p);
+  CU(cudaMemcpyAsync(s->staging.p, s->accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
   for (size_t i = 0; i < n; i++) {  // `row[i] = row[i] + color` (Q24): accumulate INTO the caller's sums
     pixels_rgb[3 * i + 0] += (double)h[i].x;
     pixels_rgb[3 * i + 1] += (double)h[i].y;

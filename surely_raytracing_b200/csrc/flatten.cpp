@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -180,9 +181,14 @@ struct BvhBuilder {
   std::vector<int> order;
   std::vector<BuildNode> nodes;
   int max_depth = 0;
-  static constexpr double kTraversal = 1.0, kIntersect = 1.5;
+  double kTraversal = 1.0, kIntersect = 3.0;  // SAH costs (RTB_BVH_CI / RTB_BVH_LEAF override, tuning runs)
+  int max_leaf = 1;  // measured on c4: one primitive per leaf, Ci/Ct = 3 -> fewest f64 tests (profiles/r01_bvh_sweep.txt)
 
-  explicit BvhBuilder(const std::vector<Baked>& p) : prims(p), order(p.size()) { std::iota(order.begin(), order.end(), 0); }
+  explicit BvhBuilder(const std::vector<Baked>& p) : prims(p), order(p.size()) {
+    std::iota(order.begin(), order.end(), 0);
+    if (const char* e = getenv("RTB_BVH_CI")) kIntersect = atof(e);
+    if (const char* e = getenv("RTB_BVH_LEAF")) max_leaf = std::max(1, std::min(8, atoi(e)));
+  }
 
   int build(int first, int count, int depth) {
     max_depth = std::max(max_depth, depth);
@@ -214,7 +220,7 @@ struct BvhBuilder {
     const double parent_area = std::max(node.box.area(), 1e-300);
     const double split_cost = kTraversal + kIntersect * best_cost / parent_area;
     const double leaf_cost = kIntersect * count;
-    if (count <= BVH_MAX_LEAF && leaf_cost <= split_cost) return self;
+    if (count <= max_leaf && leaf_cost <= split_cost) return self;
     std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
       return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
     });

@@ -13,10 +13,15 @@ cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, 
                                bool collect_stats, cudaStream_t stream, int* launches);
 
 // wavefront pipeline: ray-gen / extend / shade+accumulate kernels over SoA ray queues
+constexpr int WF_MAX_SUB = 4;
 struct WavefrontContext {   // per-scene host state of the wavefront driver
-  void* host_counters;      // pinned mirror of the device counters
+  void* host_counters;      // pinned mirrors of the device counters (one per sub-pipeline)
   int sms;
   int extend_blocks_per_sm[2];
+  int n_sub;                // sub-pipelines (streams) the stratum range is split over
+  cudaStream_t streams[WF_MAX_SUB];
+  cudaEvent_t ev_done[WF_MAX_SUB];
+  cudaEvent_t ev_start;
 };
 cudaError_t wavefront_context_create(WavefrontContext* ctx);
 void wavefront_context_destroy(WavefrontContext* ctx);

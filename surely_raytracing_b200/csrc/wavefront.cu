@@ -90,9 +90,11 @@ constexpr uint32_t PADDING_PIXEL = 0xFFFFFFFFu;  // inert lane of a border tile
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-size_t wavefront_workspace_bytes(const DScene&, int64_t n) {
+static size_t queue_bytes(int64_t n) {
   return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up(sizeof(WFCounters));
 }
+// room for up to WF_MAX_SUB sub-pipelines that share `n` path slots (alignment slack per sub-pipeline)
+size_t wavefront_workspace_bytes(const DScene&, int64_t n) { return queue_bytes(n) + WF_MAX_SUB * 4096; }
 
 static WFQueues carve(void* ws, int64_t n) {
   char* p = static_cast<char*>(ws);
@@ -436,9 +438,23 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, 3) k_wf_shade(const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+__global__ void k_wf_sum_segments(WFQueues Q0, WFQueues Q1, WFQueues Q2, WFQueues Q3, int n, DStats* stats) {
+  const WFQueues* q[4] = {&Q0, &Q1, &Q2, &Q3};
+  unsigned long long s = 0;
+  for (int k = 0; k < n; k++) s += q[k]->c->segments;
+  stats->segments = s;
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
 cudaError_t wavefront_context_create(WavefrontContext* ctx) {
-  ctx->host_counters = nullptr;
-  cudaError_t e = cudaMallocHost(&ctx->host_counters, sizeof(WFCounters));
+  *ctx = WavefrontContext{};
+  cudaError_t e = cudaMallocHost(&ctx->host_counters, WF_MAX_SUB * sizeof(WFCounters));
   if (e != cudaSuccess) return e;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -447,77 +463,123 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
   ctx->extend_blocks_per_sm[0] = ctx->extend_blocks_per_sm[1] = 4;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[0], k_wf_extend<false>, WF_EXTEND_BLOCK, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[1], k_wf_extend<true>, WF_EXTEND_BLOCK, 0);
+  // Sub-pipelines: independent slices of the stratum range on their own streams (RTB_WF_STREAMS).
+  // Measured on c4 (profiles/r01_streams_sweep.txt): 2-4 streams are 1-9 % SLOWER than one -- the
+  // persistent extend grid owns the register file, so the other stream's kernels queue behind it.
+  // Default 1; the path stays for scenes whose stages might complement each other better.
+  ctx->n_sub = env_int("RTB_WF_STREAMS", 1, 1, WF_MAX_SUB);
+  for (int k = 0; k < ctx->n_sub; k++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->streams[k], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
 void wavefront_context_destroy(WavefrontContext* ctx) {
   if (ctx->host_counters) cudaFreeHost(ctx->host_counters);
-  ctx->host_counters = nullptr;
+  for (int k = 0; k < WF_MAX_SUB; k++) {
+    if (ctx->streams[k]) cudaStreamDestroy(ctx->streams[k]);
+    if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+  }
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  *ctx = WavefrontContext{};
 }
 
 cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx, int64_t s_begin, int64_t s_end,
                                     float4* d_accum, DStats* d_stats, bool collect_stats, void* d_workspace,
                                     size_t workspace_bytes, int64_t capacity, cudaStream_t stream, int* launches) {
   if (workspace_bytes < wavefront_workspace_bytes(S, capacity)) return cudaErrorInvalidValue;
-  WFQueues Q = carve(d_workspace, capacity);
-  const unsigned long long tiles = (unsigned long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
-  const unsigned long long total = tiles * 32ull * (unsigned long long)(s_end - s_begin);
-  const int per_sm = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
-  const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
-  const unsigned blocks256 = (unsigned)((capacity + 255) / 256);
-  const unsigned shade_blocks = (unsigned)((capacity + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
-  int n_launch = 0;
-  k_wf_init<<<1, 1, 0, stream>>>(Q, total);
-  n_launch++;
-  RayRec* in = Q.rays_a;
-  RayRec* out = Q.rays_b;
-  WFCounters* h_c = static_cast<WFCounters*>(ctx.host_counters);  // pinned mirror for the (sparse) host polls
-  cudaError_t e = cudaSuccess;
-  // RTB_WF_PROFILE=1: per-stage CUDA-event totals on stderr (analysis runs only; adds event overhead)
+  // RTB_WF_PROFILE=1: one pipeline, per-stage CUDA-event totals on stderr (analysis runs only)
   static const bool profile = getenv("RTB_WF_PROFILE") != nullptr;
-  cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  double stage_ms[4] = {0., 0., 0., 0.};
+  const long long n_strata = (long long)(s_end - s_begin);
+  int K = profile ? 1 : ctx.n_sub;
+  if (n_strata < K) K = (int)n_strata;
+  if (K < 1) return cudaSuccess;
+  const int64_t cap = (capacity / K) & ~(int64_t)255;
+  const unsigned long long tiles = (unsigned long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
+  const int occ = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
+  const int per_sm = env_int("RTB_WF_EXTEND_BLOCKS", (occ + K - 1) / K, 1, 32);
+  const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
+  const unsigned gen_blocks = (unsigned)((cap + 255) / 256);
+  const unsigned shade_blocks = (unsigned)((cap + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
+
+  struct Sub { WFQueues Q; RayRec* in; RayRec* out; cudaStream_t st; long long s0; bool active; };
+  Sub sub[WF_MAX_SUB];
+  const size_t sub_bytes = queue_bytes(cap);
+  if ((size_t)K * sub_bytes > workspace_bytes) return cudaErrorInvalidValue;
+  cudaError_t e = cudaEventRecord(ctx.ev_start, stream);
+  if (e != cudaSuccess) return e;
+  int n_launch = 0;
+  for (int k = 0; k < K; k++) {
+    Sub& u = sub[k];
+    u.Q = carve(static_cast<char*>(d_workspace) + (size_t)k * sub_bytes, cap);
+    u.in = u.Q.rays_a;
+    u.out = u.Q.rays_b;
+    u.st = profile ? stream : ctx.streams[k];
+    u.active = true;
+    const long long lo = n_strata * k / K, hi = n_strata * (k + 1) / K;
+    u.s0 = (long long)s_begin + lo;
+    if (!profile && (e = cudaStreamWaitEvent(u.st, ctx.ev_start, 0)) != cudaSuccess) return e;
+    k_wf_init<<<1, 1, 0, u.st>>>(u.Q, tiles * 32ull * (unsigned long long)(hi - lo));
+    n_launch++;
+  }
+  WFCounters* h_c = static_cast<WFCounters*>(ctx.host_counters);  // pinned mirrors for the (sparse) host polls
+  cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+  double stage_ms[3] = {0., 0., 0.};
   if (profile)
     for (auto& ev : pe) cudaEventCreate(&ev);
   const int poll_every = profile ? 1 : 8;
-  for (long long iter = 0;; iter++) {
-    // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue
-    if (profile) cudaEventRecord(pe[0], stream);
-    k_wf_generate<<<blocks256, 256, 0, stream>>>(S, Q, (long long)s_begin, out);
-    k_wf_advance<<<1, 1, 0, stream>>>(Q);
-    if (profile) cudaEventRecord(pe[1], stream);
-    { RayRec* t = in; in = out; out = t; }
-    if (collect_stats) {
-      k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
-      if (profile) { cudaEventRecord(pe[2], stream); cudaEventRecord(pe[3], stream); }
-      k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
-    } else {
-      k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, stream>>>(S, Q, in, d_stats);
-      if (profile) { cudaEventRecord(pe[2], stream); cudaEventRecord(pe[3], stream); }
-      k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, stream>>>(S, Q, in, out, d_accum, d_stats);
+  int n_active = K;
+  long long iters = 0;
+  for (long long iter = 0; n_active > 0; iter++) {
+    for (int k = 0; k < K; k++) {
+      Sub& u = sub[k];
+      if (!u.active) continue;
+      // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue
+      if (profile) cudaEventRecord(pe[0], u.st);
+      k_wf_generate<<<gen_blocks, 256, 0, u.st>>>(S, u.Q, u.s0, u.out);
+      k_wf_advance<<<1, 1, 0, u.st>>>(u.Q);
+      if (profile) cudaEventRecord(pe[1], u.st);
+      { RayRec* t = u.in; u.in = u.out; u.out = t; }
+      if (collect_stats) k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+      else k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+      if (profile) cudaEventRecord(pe[2], u.st);
+      if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+      else k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+      if (profile) {
+        cudaEventRecord(pe[3], u.st);
+        cudaEventSynchronize(pe[3]);
+        for (int j = 0; j < 3; j++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[j], pe[j + 1]); stage_ms[j] += ms; }
+      }
+      n_launch += 4;
     }
-    if (profile) {
-      cudaEventRecord(pe[4], stream);
-      cudaEventSynchronize(pe[4]);
-      for (int k = 0; k < 4; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[k], pe[k + 1]); stage_ms[k] += ms; }
-    }
-    n_launch += 4;
+    iters++;
     if ((iter % poll_every) == poll_every - 1) {
-      e = cudaMemcpyAsync(h_c, Q.c, sizeof(WFCounters), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess) return e;
-      if (h_c->next_path >= h_c->total_paths && h_c->n_out == 0) break;
+      for (int k = 0; k < K; k++)
+        if (sub[k].active && (e = cudaMemcpyAsync(h_c + k, sub[k].Q.c, sizeof(WFCounters), cudaMemcpyDeviceToHost, sub[k].st)) != cudaSuccess) return e;
+      for (int k = 0; k < K; k++) {
+        if (!sub[k].active) continue;
+        if ((e = cudaStreamSynchronize(sub[k].st)) != cudaSuccess) return e;
+        if (h_c[k].next_path >= h_c[k].total_paths && h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
+      }
     }
   }
   if (profile) {
-    fprintf(stderr, "[rtb wavefront] iterations %d  segments %llu  generate %.2f ms  extend %.2f ms  resolve %.2f ms  shade %.2f ms\n",
-            (n_launch - 1) / 4, (unsigned long long)h_c->segments, stage_ms[0], stage_ms[1], stage_ms[2], stage_ms[3]);
+    fprintf(stderr, "[rtb wavefront] iterations %lld  segments %llu  generate %.2f ms  extend %.2f ms  shade %.2f ms\n", iters,
+            (unsigned long long)h_c[0].segments, stage_ms[0], stage_ms[1], stage_ms[2]);
     for (auto& ev : pe) cudaEventDestroy(ev);
+  } else {
+    for (int k = 0; k < K; k++) {
+      if ((e = cudaEventRecord(ctx.ev_done[k], sub[k].st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(stream, ctx.ev_done[k], 0)) != cudaSuccess) return e;
+    }
   }
-  if (collect_stats)
-    e = cudaMemcpyAsync(&d_stats->segments, &Q.c->segments, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
+  if (collect_stats) {
+    k_wf_sum_segments<<<1, 1, 0, stream>>>(sub[0].Q, sub[K > 1 ? 1 : 0].Q, sub[K > 2 ? 2 : 0].Q, sub[K > 3 ? 3 : 0].Q, K, d_stats);
+    n_launch++;
+  }
   if (launches) *launches += n_launch;
-  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
