@@ -60,8 +60,18 @@ def build_scenes_library(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def build_example(force: bool = False, verbose: bool = False) -> Path:
+    """host/example_cornell: a main.rs-style scene on the C++ mirror, linked against librtb200.so."""
+    out = PKG / "example_cornell"
+    src = PKG / "host" / "example_cornell.cpp"
+    deps = [src, PKG / "host" / "rtb" / "scene.hpp", PKG / "host" / "rtb" / "render.hpp", PKG / "librtb200.so"]
+    if force or _stale(out, deps):
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-o", out, src, f"-L{PKG}", "-lrtb200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN"], verbose)
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return [build_cuda_library(force, verbose), build_scenes_library(force, verbose)]
+    return [build_cuda_library(force, verbose), build_scenes_library(force, verbose), build_example(force, verbose)]
 
 
 if __name__ == "__main__":
