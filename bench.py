@@ -35,7 +35,7 @@ L2_FLUSH_BYTES = 256 << 20
 # Algorithmic lane-instruction constants per call (fp32-issue-slot equivalents; DFMA/DADD/DMUL = 2
 # slots on B200, whose FP64 pipe issues at half the FP32 rate).  Derived from the SASS of
 # librtb200.so (see DESIGN.md "Roofline"); frozen here so the bench JSON is self-describing.
-I_CONST = {"node_visit": 52.0, "prim_test": 72.0, "medium_probe": 150.0, "segment_shade": 260.0, "path_setup": 140.0}
+I_CONST = {"node_visit": 78.0, "prim_test": 150.0, "medium_probe": 45.0, "segment_shade": 260.0, "path_setup": 140.0}
 PEAK_LANE_INSTR_PER_CLK_PER_SM = 128
 
 
@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
                 "node_visits_per_segment": st["node_visits"] / st["segments"],
                 "prim_tests_per_segment": st["prim_tests"] / st["segments"],
                 "medium_probes_per_segment": st["medium_probes"] / st["segments"],
-                "kernel": "k_render_mega" if pipeline != capi.PIPELINE_WAVEFRONT else "k_wf_extend",
+                "kernel": "k_render_mega" if pipeline == capi.PIPELINE_MEGAKERNEL else "k_wf_extend (+ k_wf_shade)",
                 "hbm_secondary": {"algorithmic_gbs": per_gpu_paths_s * seg_per_path * 176 / 1e9,
                                   "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)), "bytes_per_segment": 176}}
         if world == 1 and not args.no_cpu_baseline:
