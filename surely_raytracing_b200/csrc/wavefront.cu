@@ -175,11 +175,14 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // fused form (t = plane * inv_d - o * inv_d), f64 reference-order primitive tests.
 // ------------------------------------------------------------------------------------------------
 constexpr int WF_EXTEND_BLOCK = 128;
+#ifndef WF_EXTEND_MIN_BLOCKS
+#define WF_EXTEND_MIN_BLOCKS 7  // 72 regs, no spills; forcing 8 blocks (64 regs) spills and measured 4 % slower
+#endif
 constexpr int WF_FETCH_THRESHOLD = 28;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
 
 template <bool STATS>
-__global__ void __launch_bounds__(WF_EXTEND_BLOCK) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
+__global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
                                                                const RayRec* __restrict__ rays_in,
                                                                DStats* __restrict__ stats) {
   const unsigned FULL = 0xFFFFFFFFu;
@@ -342,12 +345,11 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, 3) k_wf_shade(const __grid_con
         PathRec p;
         unpack_geom(it.a, it.b, it.c, p);
         unpack_state(it.d, p);
-        const Ray r = to_ray(p);
         Rand4 u;
         for (int mi = 0; mi < S.n_media; mi++) {
           if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
           const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-          const double tm = medium_event(S, mi, r, 0.0001, it.t, U);
+          const double tm = medium_event_lazy(S, mi, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
           if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
         }
       }

@@ -19,12 +19,12 @@ sys.path.insert(0, str(ROOT))
 OUT = Path(__file__).resolve().parent
 
 GOLDEN_RENDERS = {  # name: (config, variant, width, spp)
-    "oracle_c1": ("c1", 0, 160, 1024),
+    "oracle_c1": ("c1", 0, 80, 1024),      # 5x5 blocks of the 400x225 config
     "oracle_c2": ("c2", 0, 120, 1024),
     "oracle_c3": ("c3", 0, 120, 1024),
     "oracle_c3_lights": ("c3", 1, 120, 1024),
-    "oracle_c4": ("c4", 0, 120, 1024),
-    "oracle_c4_lights": ("c4", 1, 120, 1024),
+    "oracle_c4": ("c4", 0, 160, 1024),     # 5x5 blocks of the 800x800 config
+    "oracle_c4_lights": ("c4", 1, 160, 1024),
     "oracle_c5": ("c5", 0, 120, 1024),
 }
 

@@ -64,3 +64,18 @@ def test_medium_intervals_and_textures_and_light_pdf():
     od[:, 4] = np.abs(od[:, 4])
     po, pe = o.eval_light_pdf(od), e.eval_light_pdf(od)
     assert np.allclose(po, pe, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("name", ["scene_three_spheres", "two_spheres", "earth", "two_perlin_spheres", "quads", "simple_light"])
+def test_remaining_main_rs_scenes(name):
+    """The other scene functions of reference src/main.rs: hollow glass via a negative
+    radius, checker / image / Perlin textures, emissive sphere + quad."""
+    b = BuiltScene(name, width=64, spp=9, variant=1 if name == "simple_light" else 0)
+    o, e = orc.OracleScene(b, use_bvh=False), EmuScene(b)
+    rays = o.camera_rays()
+    mism, t_rel, dn, duv = util.hit_errors(o.trace(rays), e.trace(rays))
+    assert mism == 0 and t_rel < 1e-9 and dn < 1e-9 and duv < 1e-9, (mism, t_rel, dn, duv)
+    so, _ = o.render(sampler=orc.SAMPLER_KEYED)
+    se, st = e.render()
+    rel = np.abs(so - se).max(axis=2) / (np.abs(so).max(axis=2) + 1e-3)
+    assert (rel > 2e-3).mean() < 0.02 and abs(so.mean() - se.mean()) < 3e-3 * so.mean(), ((rel > 2e-3).mean(), so.mean(), se.mean())

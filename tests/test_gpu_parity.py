@@ -199,3 +199,42 @@ def test_cpp_drop_in_example_writes_the_same_ppm_as_the_python_path(tmp_path):
     ours = g.write_color(s, g.info.spp_used)
     # wavefront accumulation order is not fixed (float atomics): allow the last digit to move
     assert np.abs(ppm.astype(int) - ours.astype(int)).max() <= 1 and (ppm != ours).mean() < 0.01
+
+
+@pytest.mark.parametrize("name", ["scene_three_spheres", "two_spheres", "earth", "two_perlin_spheres", "quads", "simple_light"])
+def test_remaining_main_rs_scenes(name):
+    """The other scene functions of reference src/main.rs through the C ABI."""
+    b = BuiltScene(name, width=160, spp=16, variant=1 if name == "simple_light" else 0)
+    o, g = orc.OracleScene(b, use_bvh=False), Scene(b)
+    rays = g.camera_rays()
+    mism, t_rel, dn, duv = util.hit_errors(o.trace(rays), g.trace(rays))
+    assert mism == 0 and t_rel < 1e-9 and dn < 1e-9 and duv < 1e-9, (mism, t_rel, dn, duv)
+    so, _ = o.render(sampler=orc.SAMPLER_KEYED)
+    for pipeline in PIPELINES:
+        sg, st = g.render(pipeline=pipeline)
+        rel = np.abs(so - sg).max(axis=2) / (np.abs(so).max(axis=2) + 1e-3)
+        assert (rel > 2e-3).mean() < 0.02 and abs(so.mean() - sg.mean()) < 3e-3 * so.mean(), (pipeline, (rel > 2e-3).mean())
+
+
+@pytest.mark.parametrize("name,cfg,variant", [("oracle_c1", "c1", 0), ("oracle_c2", "c2", 0), ("oracle_c3", "c3", 0),
+                                               ("oracle_c4", "c4", 0), ("oracle_c5", "c5", 0)])
+def test_full_size_configs_against_the_oracle_statistics(name, cfg, variant):
+    """BASELINE.json's configs at their FULL resolution and (for c1/c2/c3/c5) full spp on the GPU; the
+    oracle cannot render these in test time, so the image is box-filtered 5x5 down to the committed
+    low-resolution oracle render -- the mean over a 5x5 pixel block of the full-size camera is the same
+    integral as one pixel of the 1/5-size camera -- and accepted with the variance-aware bound.
+    c4 runs 400 of its 10000 strata (16 full stratum rows; the estimator is unbiased for any subset)."""
+    gold = np.load(util.GOLDEN / f"{name}.npz")
+    b = BuiltScene(cfg, variant=variant)            # BASELINE defaults: full width / spp / depth
+    g = Scene(b)
+    H, W = g.info.image_height, g.info.image_width
+    gh, gw = gold["mean"].shape[:2]
+    assert (H // 5, W // 5) == (gh, gw) and g.info.spp_used in (49, 961, 1936, 10000)
+    n = g.info.spp_used if cfg != "c4" else 400
+    sg, st = g.render(0, n)
+    assert st["paths"] == H * W * n and st["nonfinite_samples"] == 0
+    mean = (sg / n)[: gh * 5, : gw * 5].reshape(gh, 5, gw, 5, 3).mean(axis=(1, 3))
+    # a 5x5 block of n-sample pixels has (about) the variance of one pixel with 25 n samples
+    ok, rep = util.image_acceptance(mean, 25 * n, gold["mean"].astype(np.float64), int(gold["spp"]), gold["var"].astype(np.float64))
+    print(name, (W, H), n, rep)
+    assert ok, rep
