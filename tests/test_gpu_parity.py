@@ -219,18 +219,19 @@ def test_remaining_main_rs_scenes(name):
 @pytest.mark.parametrize("name,cfg,variant", [("oracle_c1", "c1", 0), ("oracle_c2", "c2", 0), ("oracle_c3", "c3", 0),
                                                ("oracle_c4", "c4", 0), ("oracle_c5", "c5", 0)])
 def test_full_size_configs_against_the_oracle_statistics(name, cfg, variant):
-    """BASELINE.json's configs at their FULL resolution and (for c1/c2/c3/c5) full spp on the GPU; the
-    oracle cannot render these in test time, so the image is box-filtered 5x5 down to the committed
-    low-resolution oracle render -- the mean over a 5x5 pixel block of the full-size camera is the same
-    integral as one pixel of the 1/5-size camera -- and accepted with the variance-aware bound.
-    c4 runs 400 of its 10000 strata (16 full stratum rows; the estimator is unbiased for any subset)."""
+    """BASELINE.json's configs at their FULL resolution and FULL spp on the GPU (c4: 800x800 @ 10000 spp =
+    6.4 G paths, the headline target).  The oracle cannot render these in test time, so the image is
+    box-filtered 5x5 down to the committed low-resolution oracle render -- the mean over a 5x5 pixel
+    block of the full-size camera is the same integral as one pixel of the 1/5-size camera -- and
+    accepted with the variance-aware bound.  (All strata are needed: a contiguous sub-range of the
+    stratified grid covers only a band of each pixel.)"""
     gold = np.load(util.GOLDEN / f"{name}.npz")
     b = BuiltScene(cfg, variant=variant)            # BASELINE defaults: full width / spp / depth
     g = Scene(b)
     H, W = g.info.image_height, g.info.image_width
     gh, gw = gold["mean"].shape[:2]
     assert (H // 5, W // 5) == (gh, gw) and g.info.spp_used in (49, 961, 1936, 10000)
-    n = g.info.spp_used if cfg != "c4" else 400
+    n = g.info.spp_used
     sg, st = g.render(0, n)
     assert st["paths"] == H * W * n and st["nonfinite_samples"] == 0
     mean = (sg / n)[: gh * 5, : gw * 5].reshape(gh, 5, gw, 5, 3).mean(axis=(1, 3))
