@@ -193,6 +193,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   D.n_prims = (int)h.prim_info.size();
   D.n_media = (int)h.media.size();
   D.n_lights = (int)h.lights.size();
+  D.bvh_depth = h.bvh_depth;
   D.flags = h.flags;
   D.seed_lo = (uint32_t)h.seed;
   D.seed_hi = (uint32_t)(h.seed >> 32);

@@ -104,6 +104,7 @@ struct DScene {
   const uint8_t* perlin_perm; // 768 per table: perm_x | perm_y | perm_z
   const DLight* lights;
   int n_nodes, n_surface_prims, n_prims, n_media, n_lights;
+  int bvh_depth;
   uint32_t flags;
   uint32_t seed_lo, seed_hi;
   DCamera cam;

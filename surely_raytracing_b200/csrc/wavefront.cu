@@ -93,8 +93,11 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t queue_bytes(int64_t n) {
   return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up(sizeof(WFCounters));
 }
+// traversal stacks of the pool extend kernel: one int[WF_POOL_STACK] per pool entry of every resident warp
+constexpr int WF_POOL_MAX_BLOCKS_PER_SM = 12;
+static size_t pool_scratch_bytes(int sms) { return align_up((size_t)sms * WF_POOL_MAX_BLOCKS_PER_SM * (128 / 32) * 64 * 32 * sizeof(int)); }
 // room for up to WF_MAX_SUB sub-pipelines that share `n` path slots (alignment slack per sub-pipeline)
-size_t wavefront_workspace_bytes(const DScene&, int64_t n) { return queue_bytes(n) + WF_MAX_SUB * 4096; }
+size_t wavefront_workspace_bytes(const DScene&, int64_t n) { return queue_bytes(n) + WF_MAX_SUB * 4096 + pool_scratch_bytes(160); }
 
 static WFQueues carve(void* ws, int64_t n) {
   char* p = static_cast<char*>(ws);
@@ -298,6 +301,203 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
 }
 
 // ------------------------------------------------------------------------------------------------
+// extend, pool variant.  ncu on k_wf_extend: 15 of 32 lanes active -- the inner loop waits for the
+// slowest descent of the warp (18 lanes) and the f64 leaf tests run split by primitive kind (6-9
+// lanes).  Here each persistent warp keeps WF_POOL rays (2 per lane) with their traversal state in
+// shared memory; every iteration the warp picks ONE phase -- inner-node steps, sphere leaves or quad
+// leaves, whichever has most entries ready -- and its 32 lanes take up to 32 entries in that phase.
+// Lanes are therefore nearly always full and a leaf pass tests one primitive kind only.  Traversal
+// stacks live in a per-warp global scratch (L1-resident, like local memory).
+// Results are bit-identical to k_wf_extend: the same tests, and closest hits do not depend on order.
+// MEASURED (profiles/r01_pool_extend.txt): lanes rise 15 -> 19 (leaf tests 6 -> 21) and warp
+// instructions drop 10 %, but the pick bookkeeping (ballots, shared-memory state round trips) and the
+// loss of back-to-back node loads cost more: 42.9 ms vs 34.5 ms per c4 step.  Kept as an opt-in
+// (RTB_WF_EXTEND_POOL=1) and as a parity cross-check of the default kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int WF_POOL = 64;        // entries per warp
+constexpr int WF_POOL_STACK = 32;  // stack entries per ray (deeper trees fall back to k_wf_extend)
+constexpr int WF_POOL_BLOCK = 128;
+constexpr int WF_POOL_WARPS = WF_POOL_BLOCK / 32;
+#ifndef WF_POOL_CHUNK_STEPS
+#define WF_POOL_CHUNK_STEPS 6
+#endif
+constexpr int WF_POOL_CHUNK = WF_POOL_CHUNK_STEPS;   // inner-node steps per pick
+enum : int { ST_EMPTY = 0, ST_INNER = 1, ST_LEAF_S = 2, ST_LEAF_Q = 3 };
+
+struct PoolWarp {
+  double ox[WF_POOL], oy[WF_POOL], oz[WF_POOL], tbest[WF_POOL];
+  float dx[WF_POOL], dy[WF_POOL], dz[WF_POOL], time[WF_POOL];
+  float idx[WF_POOL], idy[WF_POOL], idz[WF_POOL], oxi[WF_POOL], oyi[WF_POOL], ozi[WF_POOL];
+  int best_prim[WF_POOL], best_kind[WF_POOL], best_id[WF_POOL];
+  int node[WF_POOL], sp[WF_POOL], pos[WF_POOL], status[WF_POOL];
+  int list[32];
+};
+
+__device__ __forceinline__ int leaf_status(const DScene& S, int node) {
+  // kind of the (first) primitive of a leaf; mixed leaves are tested by test_prim anyway
+  const int first = (~node) >> 3;
+  return (__ldg(S.prim_info + first).x & 0xFF) == PRIM_QUAD ? ST_LEAF_Q : ST_LEAF_S;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_constant__ DScene S, WFQueues Q,
+                                                                 const RayRec* __restrict__ rays_in,
+                                                                 int* __restrict__ stack_scratch,
+                                                                 DStats* __restrict__ stats) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  __shared__ PoolWarp pool[WF_POOL_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PoolWarp& W = pool[warp];
+  int* const stacks = stack_scratch + ((size_t)(blockIdx.x * WF_POOL_WARPS + warp) * WF_POOL) * WF_POOL_STACK;
+  const int n = Q.c->n_in;
+  const unsigned lt = (1u << lane) - 1u;
+  const float tmin32 = __double2float_rd(0.0001);
+  const bool any_surface = S.n_surface_prims > 0;
+  unsigned long long st_nodes = 0, st_prims = 0;
+  W.status[lane] = ST_EMPTY;
+  W.status[lane + 32] = ST_EMPTY;
+  bool exhausted = false;
+  __syncwarp();
+  for (;;) {
+    int s0 = W.status[lane], s1 = W.status[lane + 32];
+    // ---- refill empty entries from the queue ---------------------------------------------------------
+    {
+      const unsigned e0 = __ballot_sync(FULL, s0 == ST_EMPTY), e1 = __ballot_sync(FULL, s1 == ST_EMPTY);
+      const int n_empty = __popc(e0) + __popc(e1);
+      if (!exhausted && n_empty >= 16) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&Q.c->extend_cursor, n_empty);
+        base = __shfl_sync(FULL, base, 0);
+        exhausted = base + n_empty >= n;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          const bool mine = half == 0 ? (s0 == ST_EMPTY) : (s1 == ST_EMPTY);
+          const int k = base + (half == 0 ? __popc(e0 & lt) : __popc(e0) + __popc(e1 & lt));
+          if (mine && k < n) {
+            const int e = lane + 32 * half;
+            const uint4* R = reinterpret_cast<const uint4*>(rays_in + k);
+            const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+            PathRec p;
+            unpack_geom(a, b, c, p);
+            if (any_surface) {
+              const float ix = 1.0f / p.dx, iy = 1.0f / p.dy, iz = 1.0f / p.dz;
+              W.ox[e] = p.ox; W.oy[e] = p.oy; W.oz[e] = p.oz;
+              W.dx[e] = p.dx; W.dy[e] = p.dy; W.dz[e] = p.dz; W.time[e] = p.time;
+              W.idx[e] = ix; W.idy[e] = iy; W.idz[e] = iz;
+              W.oxi[e] = (float)p.ox * ix; W.oyi[e] = (float)p.oy * iy; W.ozi[e] = (float)p.oz * iz;
+              W.tbest[e] = RTB_INF;
+              W.best_prim[e] = -1; W.best_kind[e] = -1; W.best_id[e] = -1;
+              W.node[e] = 0; W.sp[e] = 0; W.pos[e] = k;
+              W.status[e] = ST_INNER;
+            } else {  // nothing to traverse: record the miss
+              HitRec h;
+              h.t = RTB_INF; h.id = -1; h.pad = 0;
+              Q.hits[k] = h;
+            }
+          }
+        }
+        __syncwarp();
+        s0 = W.status[lane]; s1 = W.status[lane + 32];
+      }
+    }
+    // ---- pick the phase with most ready entries ---------------------------------------------------------
+    const unsigned i0 = __ballot_sync(FULL, s0 == ST_INNER), i1 = __ballot_sync(FULL, s1 == ST_INNER);
+    const unsigned p0 = __ballot_sync(FULL, s0 == ST_LEAF_S), p1 = __ballot_sync(FULL, s1 == ST_LEAF_S);
+    const unsigned q0 = __ballot_sync(FULL, s0 == ST_LEAF_Q), q1 = __ballot_sync(FULL, s1 == ST_LEAF_Q);
+    const int nI = __popc(i0) + __popc(i1), nS = __popc(p0) + __popc(p1), nQ = __popc(q0) + __popc(q1);
+    if (nI + nS + nQ == 0) {
+      if (exhausted) break;
+      continue;  // everything empty but rays remain: the refill above runs next turn (n_empty == 64)
+    }
+    int phase;
+    unsigned m0, m1;
+    if (nI >= 32 || (nI >= nS && nI >= nQ)) { phase = ST_INNER; m0 = i0; m1 = i1; }
+    else if (nS >= nQ) { phase = ST_LEAF_S; m0 = p0; m1 = p1; }
+    else { phase = ST_LEAF_Q; m0 = q0; m1 = q1; }
+    {
+      const int r0 = __popc(m0 & lt), r1 = __popc(m0) + __popc(m1 & lt);
+      if (((m0 >> lane) & 1u) && r0 < 32) W.list[r0] = lane;
+      if (((m1 >> lane) & 1u) && r1 < 32) W.list[r1] = lane + 32;
+    }
+    const int cnt = min(32, __popc(m0) + __popc(m1));
+    __syncwarp();
+    if (lane < cnt) {
+      const int e = W.list[lane];
+      int* const stack = stacks + e * WF_POOL_STACK;
+      int node = W.node[e], sp = W.sp[e];
+      if (phase == ST_INNER) {
+        const float idx = W.idx[e], idy = W.idy[e], idz = W.idz[e];
+        const float oxi = W.oxi[e], oyi = W.oyi[e], ozi = W.ozi[e];
+        const float tbest32 = __double2float_ru(W.tbest[e]);
+#pragma unroll 1
+        for (int step = 0; step < WF_POOL_CHUNK && node >= 0 && node != TRAV_DONE; step++) {
+          if (STATS) st_nodes++;
+          const float4* N = S.nodes + 4 * (size_t)node;
+          const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+          float a0 = fmaf(n0.x, idx, -oxi), a1 = fmaf(n0.y, idx, -oxi);
+          float b0 = fmaf(n0.z, idy, -oyi), b1 = fmaf(n0.w, idy, -oyi);
+          float c0 = fmaf(n2.x, idz, -ozi), c1 = fmaf(n2.y, idz, -ozi);
+          const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+          const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+          a0 = fmaf(n1.x, idx, -oxi); a1 = fmaf(n1.y, idx, -oxi);
+          b0 = fmaf(n1.z, idy, -oyi); b1 = fmaf(n1.w, idy, -oyi);
+          c0 = fmaf(n2.z, idz, -ozi); c1 = fmaf(n2.w, idz, -ozi);
+          const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+          const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+          const bool h0 = tn0 <= fmaf(fabsf(tf0), 4e-6f, tf0);
+          const bool h1 = tn1 <= fmaf(fabsf(tf1), 4e-6f, tf1);
+          int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+          if (h0 && h1) {
+            if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
+            stack[sp++] = ch1;
+            node = ch0;
+          } else if (h0) {
+            node = ch0;
+          } else if (h1) {
+            node = ch1;
+          } else {
+            node = sp > 0 ? stack[--sp] : TRAV_DONE;
+          }
+        }
+      } else {
+        // ---- leaf: f64 reference-order tests of one primitive kind ----------------------------------------
+        Ray r;
+        r.ox = W.ox[e]; r.oy = W.oy[e]; r.oz = W.oz[e];
+        r.dx = (double)W.dx[e]; r.dy = (double)W.dy[e]; r.dz = (double)W.dz[e]; r.time = (double)W.time[e];
+        Hit best;
+        best.t = W.tbest[e]; best.a = 0.; best.b = 0.;
+        best.prim = W.best_prim[e]; best.kind = W.best_kind[e]; best.id = W.best_id[e];
+        const int l = ~node;
+        const int first = l >> 3, count = (l & 7) + 1;
+        for (int i = 0; i < count; i++) {
+          if (STATS) st_prims++;
+          test_prim(S, first + i, r, 0.0001, best);
+        }
+        W.tbest[e] = best.t;
+        W.best_prim[e] = best.prim; W.best_kind[e] = best.kind; W.best_id[e] = best.id;
+        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+      }
+      // ---- write the entry back / retire it -------------------------------------------------------------------
+      if (node == TRAV_DONE) {
+        HitRec h;
+        h.t = W.tbest[e]; h.id = W.best_prim[e]; h.pad = 0;
+        Q.hits[W.pos[e]] = h;
+        W.status[e] = ST_EMPTY;
+      } else {
+        W.node[e] = node;
+        W.sp[e] = sp;
+        W.status[e] = node >= 0 ? ST_INNER : leaf_status(S, node);
+      }
+    }
+    __syncwarp();
+  }
+  if (STATS) {
+    atomicAdd(&stats->node_visits, st_nodes);
+    atomicAdd(&stats->prim_tests, st_prims);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // shade (fused resolve + sort + shade).  One block owns WF_SHADE_BLOCK consecutive queue positions:
 //   1. stream the ray + hit records in (coalesced), add the constant-medium events
 //      (ConstantMedium::hit, constant_medium.rs:41-95) and look up the shading class;
@@ -307,7 +507,13 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
 //      queue with one atomic per block, finished paths add their radiance to the image.
 // No global bins, no gathers: every global access of this kernel is sequential.
 // ------------------------------------------------------------------------------------------------
-constexpr int WF_SHADE_BLOCK = 256;
+#ifndef WF_SHADE_BLOCK_DIM
+#define WF_SHADE_BLOCK_DIM 256
+#endif
+#ifndef WF_SHADE_MIN_BLOCKS
+#define WF_SHADE_MIN_BLOCKS 3
+#endif
+constexpr int WF_SHADE_BLOCK = WF_SHADE_BLOCK_DIM;
 constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
 
 struct ShadeItem {  // what moves through shared memory to the lane that shades it (80 B)
@@ -318,7 +524,7 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(WF_SHADE_BLOCK, 3) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
+__global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
                                                             DStats* __restrict__ stats) {
@@ -465,6 +671,10 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
   ctx->extend_blocks_per_sm[0] = ctx->extend_blocks_per_sm[1] = 4;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[0], k_wf_extend<false>, WF_EXTEND_BLOCK, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[1], k_wf_extend<true>, WF_EXTEND_BLOCK, 0);
+  ctx->pool_blocks_per_sm[0] = ctx->pool_blocks_per_sm[1] = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[0], k_wf_extend_pool<false>, WF_POOL_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[1], k_wf_extend_pool<true>, WF_POOL_BLOCK, 0);
+  ctx->extend_kind = env_int("RTB_WF_EXTEND_POOL", 0, 0, 1);  // measured slower on c4: profiles/r01_pool_extend.txt
   // Sub-pipelines: independent slices of the stratum range on their own streams (RTB_WF_STREAMS).
   // Measured on c4 (profiles/r01_streams_sweep.txt): 2-4 streams are 1-9 % SLOWER than one -- the
   // persistent extend grid owns the register file, so the other stream's kernels queue behind it.
@@ -503,13 +713,20 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   const int occ = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
   const int per_sm = env_int("RTB_WF_EXTEND_BLOCKS", (occ + K - 1) / K, 1, 32);
   const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
+  // pool extend: needs the stacks to fit WF_POOL_STACK; one sub-pipeline only (it owns the scratch)
+  const bool use_pool = ctx.extend_kind == 1 && K == 1 && S.bvh_depth + 2 <= WF_POOL_STACK && ctx.sms <= 160;
+  int pool_per_sm = ctx.pool_blocks_per_sm[collect_stats ? 1 : 0];
+  pool_per_sm = env_int("RTB_WF_POOL_BLOCKS", pool_per_sm < 1 ? 1 : pool_per_sm, 1, WF_POOL_MAX_BLOCKS_PER_SM);
+  if (pool_per_sm > WF_POOL_MAX_BLOCKS_PER_SM) pool_per_sm = WF_POOL_MAX_BLOCKS_PER_SM;
+  const unsigned pool_grid = (unsigned)(ctx.sms * pool_per_sm);
+  int* const pool_scratch = reinterpret_cast<int*>(static_cast<char*>(d_workspace) + workspace_bytes - pool_scratch_bytes(160));
   const unsigned gen_blocks = (unsigned)((cap + 255) / 256);
   const unsigned shade_blocks = (unsigned)((cap + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
 
   struct Sub { WFQueues Q; RayRec* in; RayRec* out; cudaStream_t st; long long s0; bool active; };
   Sub sub[WF_MAX_SUB];
   const size_t sub_bytes = queue_bytes(cap);
-  if ((size_t)K * sub_bytes > workspace_bytes) return cudaErrorInvalidValue;
+  if ((size_t)K * sub_bytes + pool_scratch_bytes(160) > workspace_bytes) return cudaErrorInvalidValue;
   cudaError_t e = cudaEventRecord(ctx.ev_start, stream);
   if (e != cudaSuccess) return e;
   int n_launch = 0;
@@ -544,8 +761,13 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
       k_wf_advance<<<1, 1, 0, u.st>>>(u.Q);
       if (profile) cudaEventRecord(pe[1], u.st);
       { RayRec* t = u.in; u.in = u.out; u.out = t; }
-      if (collect_stats) k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
-      else k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+      if (use_pool) {
+        if (collect_stats) k_wf_extend_pool<true><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
+        else k_wf_extend_pool<false><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
+      } else {
+        if (collect_stats) k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        else k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+      }
       if (profile) cudaEventRecord(pe[2], u.st);
       if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
       else k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);

@@ -37,7 +37,7 @@ void* emu_scene_create(const RtbSceneDesc* d) {
   D.media = h.media.data(); D.materials = h.materials.data(); D.textures = h.textures.data(); D.texels = h.texels.data();
   D.perlin_vec = h.perlin_vec.data(); D.perlin_perm = h.perlin_perm.data(); D.lights = h.lights.data();
   D.n_nodes = (int)h.nodes.size() / 4; D.n_surface_prims = h.n_surface_prims; D.n_prims = (int)h.prim_info.size();
-  D.n_media = (int)h.media.size(); D.n_lights = (int)h.lights.size();
+  D.n_media = (int)h.media.size(); D.n_lights = (int)h.lights.size(); D.bvh_depth = h.bvh_depth;
   D.flags = h.flags; D.seed_lo = (uint32_t)h.seed; D.seed_hi = (uint32_t)(h.seed >> 32);
   D.cam = h.cam;
   return e;
