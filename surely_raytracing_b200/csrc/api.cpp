@@ -34,36 +34,20 @@ int cuda_err(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_err(e__, #call); \
   } while (0)
 
-template <typename T>
-cudaError_t upload(const std::vector<T>& v, const T** d_ptr, std::vector<void*>& owned) {
-  *d_ptr = nullptr;
-  const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);  // never a null device pointer
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) return e;
-  owned.push_back(p);
-  if (!v.empty()) {
-    e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-  }
-  *d_ptr = static_cast<const T*>(p);
-  return cudaSuccess;
-}
-
 // Process-wide cache of the large buffers (wavefront workspace, pinned download staging), keyed by
 // device: render_par-style callers create and destroy a scene per image, and re-allocating ~0.7 GB
 // for each call would dominate short renders.  Freed at process exit.
 struct BigBufferCache {
   std::mutex mu;
-  struct Entry { int device; void* p; size_t bytes; bool pinned; bool in_use; };
+  struct Entry { int device; int tag; void* p; size_t bytes; bool pinned; bool in_use; };
   std::vector<Entry> entries;
-  void* acquire(int device, size_t bytes, bool pinned, size_t* got, cudaError_t* err) {
+  void* acquire(int device, int tag, size_t bytes, bool pinned, size_t* got, cudaError_t* err) {
     std::lock_guard<std::mutex> lk(mu);
     *err = cudaSuccess;
     for (Entry& e : entries)
-      if (!e.in_use && e.device == device && e.pinned == pinned && e.bytes >= bytes) { e.in_use = true; *got = e.bytes; return e.p; }
+      if (!e.in_use && e.device == device && e.tag == tag && e.pinned == pinned && e.bytes >= bytes) { e.in_use = true; *got = e.bytes; return e.p; }
     for (size_t i = 0; i < entries.size(); i++)  // drop an idle, too-small buffer of the same kind
-      if (!entries[i].in_use && entries[i].device == device && entries[i].pinned == pinned) {
+      if (!entries[i].in_use && entries[i].device == device && entries[i].tag == tag && entries[i].pinned == pinned) {
         if (pinned) cudaFreeHost(entries[i].p); else cudaFree(entries[i].p);
         entries.erase(entries.begin() + i);
         break;
@@ -71,7 +55,7 @@ struct BigBufferCache {
     void* p = nullptr;
     *err = pinned ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
     if (*err != cudaSuccess) return nullptr;
-    entries.push_back(Entry{device, p, bytes, pinned, true});
+    entries.push_back(Entry{device, tag, p, bytes, pinned, true});
     *got = bytes;
     return p;
   }
@@ -86,12 +70,13 @@ BigBufferCache& big_cache() { static BigBufferCache c; return c; }
 struct CachedBuffer {  // a lease on a BigBufferCache entry
   void* p = nullptr;
   size_t bytes = 0;
-  cudaError_t reserve(int device, size_t n, bool pinned) {
+  // `tag` keeps buffer classes apart (a freed 0.7 GB workspace must not be leased as a 2 MB scene block)
+  cudaError_t reserve(int device, int tag, size_t n, bool pinned) {
     if (n <= bytes) return cudaSuccess;
     if (p) big_cache().release(p);
     p = nullptr; bytes = 0;
     cudaError_t e;
-    p = big_cache().acquire(device, n, pinned, &bytes, &e);
+    p = big_cache().acquire(device, tag, n, pinned, &bytes, &e);
     return e;
   }
   ~CachedBuffer() { if (p) big_cache().release(p); }
@@ -117,12 +102,14 @@ struct rtb_scene {
   int device = 0;
   HostScene host;
   DScene dev{};
-  std::vector<void*> owned;
-  DeviceBuffer accum;      // float4[w*h]
+  CachedBuffer accum;      // float4[w*h]
   DeviceBuffer stats;      // DStats
   DeviceBuffer scratch_a;  // harness inputs
   DeviceBuffer scratch_b;  // harness outputs
   DeviceBuffer scratch_c;
+  CachedBuffer scene_dev;  // all scene arrays, one block
+  CachedBuffer scene_host; // pinned staging of that block
+  size_t upload_bytes = 0;
   CachedBuffer workspace;  // wavefront queues (leased from the process-wide cache)
   CachedBuffer staging;    // pinned host staging of the accumulation buffer
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -131,7 +118,6 @@ struct rtb_scene {
   RtbStats last{};
   bool stats_pending = false;
   ~rtb_scene() {
-    for (void* p : owned) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (wf_ready) wavefront_context_destroy(&wf);
@@ -169,25 +155,50 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   if (e != cudaSuccess) { delete s; return cuda_err(e, "cudaSetDevice"); }
   const HostScene& h = s->host;
   DScene& D = s->dev;
-  std::vector<double2> prims2(h.prims.size() / 2);
-  std::memcpy(prims2.data(), h.prims.data(), h.prims.size() * sizeof(double));
-#define UP(vec, field)                                              \
-  if ((e = upload(vec, &D.field, s->owned)) != cudaSuccess) {       \
-    delete s;                                                       \
-    return cuda_err(e, "upload " #field);                           \
+  // One packed upload: every scene array goes into ONE pinned staging block and ONE device block
+  // (both leased from the process-wide cache), copied with a single cudaMemcpyAsync.
+  {
+    struct Part { const void* src; size_t bytes; size_t off; };
+    Part parts[11] = {
+        {h.nodes.data(), h.nodes.size() * sizeof(float4), 0},
+        {h.prims.data(), h.prims.size() * sizeof(double), 0},
+        {h.prim_info.data(), h.prim_info.size() * sizeof(int4), 0},
+        {h.xforms.data(), h.xforms.size() * sizeof(double2), 0},
+        {h.media.data(), h.media.size() * sizeof(DMedium), 0},
+        {h.materials.data(), h.materials.size() * sizeof(DMaterial), 0},
+        {h.textures.data(), h.textures.size() * sizeof(DTexture), 0},
+        {h.texels.data(), h.texels.size(), 0},
+        {h.perlin_vec.data(), h.perlin_vec.size() * sizeof(float4), 0},
+        {h.perlin_perm.data(), h.perlin_perm.size(), 0},
+        {h.lights.data(), h.lights.size() * sizeof(DLight), 0},
+    };
+    size_t total = 0;
+    for (Part& p : parts) { p.off = total; total += (std::max<size_t>(p.bytes, 16) + 255) & ~(size_t)255; }
+    if ((e = s->scene_dev.reserve(device, 0, total, false)) != cudaSuccess || (e = s->scene_host.reserve(device, 1, total, true)) != cudaSuccess) {
+      delete s;
+      return cuda_err(e, "scene buffers");
+    }
+    char* hp = static_cast<char*>(s->scene_host.p);
+    for (const Part& p : parts)
+      if (p.bytes) std::memcpy(hp + p.off, p.src, p.bytes);
+    if ((e = cudaMemcpyAsync(s->scene_dev.p, hp, total, cudaMemcpyHostToDevice, 0)) != cudaSuccess || (e = cudaStreamSynchronize(0)) != cudaSuccess) {
+      delete s;
+      return cuda_err(e, "scene upload");
+    }
+    const char* dp = static_cast<const char*>(s->scene_dev.p);
+    D.nodes = reinterpret_cast<const float4*>(dp + parts[0].off);
+    D.prims = reinterpret_cast<const double2*>(dp + parts[1].off);
+    D.prim_info = reinterpret_cast<const int4*>(dp + parts[2].off);
+    D.xforms = reinterpret_cast<const double2*>(dp + parts[3].off);
+    D.media = reinterpret_cast<const DMedium*>(dp + parts[4].off);
+    D.materials = reinterpret_cast<const DMaterial*>(dp + parts[5].off);
+    D.textures = reinterpret_cast<const DTexture*>(dp + parts[6].off);
+    D.texels = reinterpret_cast<const uint8_t*>(dp + parts[7].off);
+    D.perlin_vec = reinterpret_cast<const float4*>(dp + parts[8].off);
+    D.perlin_perm = reinterpret_cast<const uint8_t*>(dp + parts[9].off);
+    D.lights = reinterpret_cast<const DLight*>(dp + parts[10].off);
+    s->upload_bytes = total;
   }
-  UP(h.nodes, nodes);
-  UP(prims2, prims);
-  UP(h.prim_info, prim_info);
-  UP(h.xforms, xforms);
-  UP(h.media, media);
-  UP(h.materials, materials);
-  UP(h.textures, textures);
-  UP(h.texels, texels);
-  UP(h.perlin_vec, perlin_vec);
-  UP(h.perlin_perm, perlin_perm);
-  UP(h.lights, lights);
-#undef UP
   D.n_nodes = (int)h.nodes.size() / 4;
   D.n_surface_prims = h.n_surface_prims;
   D.n_prims = (int)h.prim_info.size();
@@ -259,7 +270,7 @@ static int render_into(rtb_scene* s, const RtbRenderParams* p, float4* d_accum, 
     if (p->pipeline != RTB_PIPELINE_MEGAKERNEL) {  // default = wavefront
       const int64_t cap = wavefront_capacity();
       const size_t ws = wavefront_workspace_bytes(s->dev, cap);
-      CU(s->workspace.reserve(s->device, ws, false));
+      CU(s->workspace.reserve(s->device, 2, ws, false));
       if (!s->wf_ready) {
         CU(wavefront_context_create(&s->wf));
         s->wf_ready = true;
@@ -312,11 +323,11 @@ int rtb_render(rtb_scene* s, const RtbRenderParams* p, double* pixels_rgb, RtbSt
   if (!pixels_rgb) return set_err(RTB_ERR_INVALID, "null pixel buffer");
   CU(cudaSetDevice(s->device));
   const size_t n = (size_t)s->host.cam.width * s->host.cam.height;
-  CU(s->accum.reserve(n * sizeof(float4)));
+  CU(s->accum.reserve(s->device, 4, n * sizeof(float4), false));
   CU(cudaMemsetAsync(s->accum.p, 0, n * sizeof(float4), 0));
   rc = render_into(s, p, static_cast<float4*>(s->accum.p), 0);
   if (rc != RTB_OK) return rc;
-  CU(s->staging.reserve(s->device, n * sizeof(float4), true));
+  CU(s->staging.reserve(s->device, 3, n * sizeof(float4), true));
   const float4* h = static_cast<const float4*>(s->staging.p);
   CU(cudaMemcpyAsync(s->staging.p, s->accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, 0));
   CU(cudaStreamSynchronize(0));

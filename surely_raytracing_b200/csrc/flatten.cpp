@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -181,6 +183,8 @@ struct BvhBuilder {
   std::vector<int> order;
   std::vector<BuildNode> nodes;
   int max_depth = 0;
+  std::vector<std::pair<double, int>> keyed;  // scratch of the exact sweep
+  std::vector<double> sweep_area;
   double kTraversal = 1.0, kIntersect = 3.0;  // SAH costs (RTB_BVH_CI / RTB_BVH_LEAF override, tuning runs)
   int max_leaf = 1;  // measured on c4: one primitive per leaf, Ci/Ct = 3 -> fewest f64 tests (profiles/r01_bvh_sweep.txt)
 
@@ -199,31 +203,105 @@ struct BvhBuilder {
     const int self = (int)nodes.size();
     nodes.push_back(node);
     if (count <= 1) return self;
-    // full-sweep SAH on the three axes (n is a few thousand: build time is irrelevant)
+    // SAH split search: exact sweep over the sorted centroids for small nodes, 32 centroid bins above
+    // (scene_create sits on the e2e path of every render_par call, so the build must stay ~ms).
     double best_cost = kInf;
     int best_axis = -1, best_split = -1;
-    std::vector<int> idx(order.begin() + first, order.begin() + first + count);
-    std::vector<double> right_area(count);
-    for (int axis = 0; axis < 3; axis++) {
-      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
-        return prims[a].lo[axis] + prims[a].hi[axis] < prims[b].lo[axis] + prims[b].hi[axis];
-      });
-      Box rb;
-      for (int i = count - 1; i > 0; i--) { rb.grow(prims[idx[i]].lo, prims[idx[i]].hi); right_area[i] = rb.area(); }
-      Box lb;
-      for (int i = 1; i < count; i++) {
-        lb.grow(prims[idx[i - 1]].lo, prims[idx[i - 1]].hi);
-        const double cost = lb.area() * i + right_area[i] * (count - i);
-        if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+    double best_plane = 0.;  // binned split: centroid*2 threshold on best_axis
+    const bool binned = count > 8;
+    if (!binned) {
+      if ((int)keyed.size() < count) { keyed.resize(count); sweep_area.resize(count); }
+      for (int axis = 0; axis < 3; axis++) {
+        for (int i = 0; i < count; i++) {
+          const int pi = order[first + i];
+          keyed[i] = {prims[pi].lo[axis] + prims[pi].hi[axis], i};  // (key, position): ties keep their order
+        }
+        std::sort(keyed.begin(), keyed.begin() + count);
+        Box rb;
+        for (int i = count - 1; i > 0; i--) {
+          const Baked& p = prims[order[first + keyed[i].second]];
+          rb.grow(p.lo, p.hi);
+          sweep_area[i] = rb.area();
+        }
+        Box lb;
+        for (int i = 1; i < count; i++) {
+          const Baked& p = prims[order[first + keyed[i - 1].second]];
+          lb.grow(p.lo, p.hi);
+          const double cost = lb.area() * i + sweep_area[i] * (count - i);
+          if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+        }
+      }
+    } else {
+      constexpr int NB = 32;
+      for (int axis = 0; axis < 3; axis++) {
+        double cmin = kInf, cmax = -kInf;
+        for (int i = 0; i < count; i++) {
+          const Baked& p = prims[order[first + i]];
+          const double c = p.lo[axis] + p.hi[axis];
+          cmin = std::min(cmin, c); cmax = std::max(cmax, c);
+        }
+        if (!(cmax > cmin)) continue;
+        Box bins[NB];
+        int cnt[NB] = {0};
+        const double scale = NB / (cmax - cmin);
+        for (int i = 0; i < count; i++) {
+          const Baked& p = prims[order[first + i]];
+          int b = (int)((p.lo[axis] + p.hi[axis] - cmin) * scale);
+          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          bins[b].grow(p.lo, p.hi);
+          cnt[b]++;
+        }
+        double right_area[NB];
+        int right_cnt[NB];
+        Box rb;
+        int rc = 0;
+        for (int b = NB - 1; b > 0; b--) { if (cnt[b]) rb.grow(bins[b].lo, bins[b].hi); rc += cnt[b]; right_area[b] = rb.area(); right_cnt[b] = rc; }
+        Box lb;
+        int lc = 0;
+        for (int b = 1; b < NB; b++) {
+          if (cnt[b - 1]) lb.grow(bins[b - 1].lo, bins[b - 1].hi);
+          lc += cnt[b - 1];
+          if (lc == 0 || right_cnt[b] == 0) continue;
+          const double cost = lb.area() * lc + right_area[b] * right_cnt[b];
+          if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = lc; best_plane = cmin + b / scale; }
+        }
+      }
+      if (best_axis < 0) {  // all centroids coincide: split by index
+        best_axis = 0; best_split = count / 2; best_cost = node.box.area() * count;
       }
     }
     const double parent_area = std::max(node.box.area(), 1e-300);
     const double split_cost = kTraversal + kIntersect * best_cost / parent_area;
     const double leaf_cost = kIntersect * count;
     if (count <= max_leaf && leaf_cost <= split_cost) return self;
-    std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
-      return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
-    });
+    if (binned && best_plane != 0.) {
+      // same bin assignment as the search (so the counts match), order inside each side kept
+      double cmin = kInf, cmax = -kInf;
+      for (int i = 0; i < count; i++) {
+        const Baked& p = prims[order[first + i]];
+        const double c = p.lo[best_axis] + p.hi[best_axis];
+        cmin = std::min(cmin, c); cmax = std::max(cmax, c);
+      }
+      const double scale = 32 / (cmax - cmin);
+      const int split_bin = (int)std::lround((best_plane - cmin) * scale);
+      auto left_side = [&](int a) {
+        int b = (int)((prims[a].lo[best_axis] + prims[a].hi[best_axis] - cmin) * scale);
+        b = b < 0 ? 0 : (b >= 32 ? 31 : b);
+        return b < split_bin;
+      };
+      auto mid = std::stable_partition(order.begin() + first, order.begin() + first + count, left_side);
+      best_split = (int)(mid - (order.begin() + first));
+      if (best_split <= 0 || best_split >= count) {  // numerical corner: fall back to a median split
+        std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
+          return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
+        });
+        best_split = count / 2;
+      }
+    } else {
+      std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
+        return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
+      });
+    }
     const int l = build(first, best_split, depth + 1);
     const int r = build(first + best_split, count - best_split, depth + 1);
     nodes[self].left = l;
@@ -273,6 +351,14 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     err = "world must be a list object";
     return RTB_ERR_INVALID;
   }
+  const bool timing = getenv("RTB_TIME_FLATTEN") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rtb flatten] %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
   out = HostScene();
   out.flags = d.flags;
   out.seed = d.seed;
@@ -329,6 +415,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     out.materials.push_back(o);
   }
 
+  lap("tables");
   // ---- object graph ---------------------------------------------------------------------------
   Builder B(d, out, err);
   if (!B.walk(d.world, Xform(), -1, 0)) return err.find("not supported") != std::string::npos ? RTB_ERR_UNSUPPORTED : RTB_ERR_INVALID;
@@ -409,10 +496,12 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   for (int a = 0; a < 3; a++) M = std::max(M, std::fabs(out.cam.center[a]));
   const double pad = M * 1e-6;
 
+  lap("walk");
   BvhBuilder bvh(B.surfaces);
   std::vector<int> node_remap;
   if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
   if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
+  lap("bvh build");
   out.bvh_depth = bvh.max_depth;
   for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
   out.n_surface_prims = (int)B.surfaces.size();
@@ -456,6 +545,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     emit_node(0);
   }
 
+  lap("emit");
   // ---- media: boundary primitives after the surfaces, in DFS order ----------------------------------
   for (size_t mi = 0; mi < B.boundaries.size(); mi++) {
     DMedium m{};
