@@ -313,6 +313,17 @@ struct BvhBuilder {
 
 inline float round_down(double x) { float f = (float)x; return ((double)f > x) ? std::nextafterf(f, -INFINITY) : f; }
 inline float round_up(double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; }
+// the two fp32 slots of one axis of a node box: outward-rounded lo / hi (default) or, in the
+// RTB_SLAB_CENTER A/B arm, centre / half-extent of a box that still contains [lo, hi]
+inline void box_center_half(double lo, double hi, float& c, float& h) {
+#if !defined(RTB_SLAB_CENTER)
+  c = round_down(lo); h = round_up(hi);
+  return;
+#endif
+  c = (float)(0.5 * (lo + hi));
+  h = round_up(std::max((double)c - lo, hi - (double)c));
+  h = std::nextafterf(h, INFINITY);
+}
 
 int shading_class(const RtbSceneDesc& d, int material) {
   const RtbMaterial& m = d.materials[material];
@@ -515,13 +526,13 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     out.nodes.resize(out.nodes.size() + 4);
     const int refs[2] = {emit_node(bn.left), emit_node(bn.right)};
     const Box* cb[2] = {&bvh.nodes[bn.left].box, &bvh.nodes[bn.right].box};
-    float lo[2][3], hi[2][3];
+    float ctr[2][3], half[2][3];
     for (int c = 0; c < 2; c++)
-      for (int a = 0; a < 3; a++) { lo[c][a] = round_down(cb[c]->lo[a] - pad); hi[c][a] = round_up(cb[c]->hi[a] + pad); }
+      for (int a = 0; a < 3; a++) box_center_half(cb[c]->lo[a] - pad, cb[c]->hi[a] + pad, ctr[c][a], half[c][a]);
     float4* N = &out.nodes[4 * (size_t)self];
-    N[0] = float4{lo[0][0], hi[0][0], lo[0][1], hi[0][1]};
-    N[1] = float4{lo[1][0], hi[1][0], lo[1][1], hi[1][1]};
-    N[2] = float4{lo[0][2], hi[0][2], lo[1][2], hi[1][2]};
+    N[0] = float4{ctr[0][0], half[0][0], ctr[0][1], half[0][1]};
+    N[1] = float4{ctr[1][0], half[1][0], ctr[1][1], half[1][1]};
+    N[2] = float4{ctr[0][2], half[0][2], ctr[1][2], half[1][2]};
     float r0, r1;
     std::memcpy(&r0, &refs[0], 4);
     std::memcpy(&r1, &refs[1], 4);
@@ -535,8 +546,10 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     // a single leaf: both children of the root reference it (the second test is a no-op by the
     // tie rule -- the reference's BvhNode::new duplicates a lone object the same way, hittable.rs:161-162)
     const Box& bx = bvh.nodes[0].box;
-    const float4 n0 = float4{round_down(bx.lo[0] - pad), round_up(bx.hi[0] + pad), round_down(bx.lo[1] - pad), round_up(bx.hi[1] + pad)};
-    const float lz = round_down(bx.lo[2] - pad), hz = round_up(bx.hi[2] + pad);
+    float c3[3], h3[3];
+    for (int a = 0; a < 3; a++) box_center_half(bx.lo[a] - pad, bx.hi[a] + pad, c3[a], h3[a]);
+    const float4 n0 = float4{c3[0], h3[0], c3[1], h3[1]};
+    const float lz = c3[2], hz = h3[2];
     const int ref0 = leaf_ref(0, bvh.nodes[0].count);
     float r0;
     std::memcpy(&r0, &ref0, 4);

@@ -210,13 +210,56 @@ RTB_DEV void test_prim(const DScene& S, int pi, const Ray& r, double tmin, Hit& 
 }
 
 // ------------------------------------------------------------------------------------------------
+// One BVH2 node = both children's boxes (4 x float4):
+//   n0 = lo0x hi0x lo0y hi0y | n1 = lo1x hi1x lo1y hi1y | n2 = lo0z hi0z lo1z hi1z | n3 = child refs
+// Slab distances in fused form: t = plane * inv_d - o * inv_d (one FFMA per plane).
+// Conservative: boxes are padded on the host, far gets a 4e-6 relative slack, NaNs are dropped by
+// fminf/fmaxf, which only ever widens the interval.
+// A/B arm RTB_SLAB_CENTER (measured, no gain: 62.9 vs 62.4 ms per c4 step): centre / half-extent
+// slots, t_mid = c * inv_d - o * inv_d, near/far = t_mid -/+ h |inv_d| -- trades the 12 per-axis
+// FMNMX of a node for 6 FFMA, but the loop is not bound by the ALU pipe alone.
+// ------------------------------------------------------------------------------------------------
+struct SlabRay { float idx, idy, idz, oxi, oyi, ozi; };
+
+// Exactly-zero direction components DO occur (r2 = 0 in the cosine map returns the surface normal,
+// e.g. (0,1,0) off the ground; about a dozen rays per 64 M paths): with 1/0 = inf the centre/extent
+// form turns those axes into NaN = "unconstrained" and the ray visits most of the tree (measured:
+// single rays stretching an extend launch from 0.47 to 3.4 ms).  A tiny non-zero stand-in keeps the
+// reciprocal finite; the slab along that axis then culls correctly and conservatively.
+RTB_DEV float safe_rcp(float d) { return 1.0f / (fabsf(d) >= 1e-20f ? d : copysignf(1e-20f, d)); }
+
+RTB_DEV SlabRay slab_ray(double ox, double oy, double oz, float dx, float dy, float dz) {
+  SlabRay s;
+  s.idx = safe_rcp(dx); s.idy = safe_rcp(dy); s.idz = safe_rcp(dz);
+  s.oxi = (float)ox * s.idx; s.oyi = (float)oy * s.idy; s.ozi = (float)oz * s.idz;
+  return s;
+}
+
+RTB_DEV void slab_box(float cx, float hx, float cy, float hy, float cz, float hz, const SlabRay& s, float tmin32,
+                      float tbest32, float& tn, bool& hit) {
+#if !defined(RTB_SLAB_CENTER)
+  const float a0 = fmaf(cx, s.idx, -s.oxi), a1 = fmaf(hx, s.idx, -s.oxi);
+  const float b0 = fmaf(cy, s.idy, -s.oyi), b1 = fmaf(hy, s.idy, -s.oyi);
+  const float c0 = fmaf(cz, s.idz, -s.ozi), c1 = fmaf(hz, s.idz, -s.ozi);
+  tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+  const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+#else
+  // A/B arm: the slots hold centre / half-extent instead of lo / hi
+  const float mx = fmaf(cx, s.idx, -s.oxi), my = fmaf(cy, s.idy, -s.oyi), mz = fmaf(cz, s.idz, -s.ozi);
+  const float ex = hx * fabsf(s.idx), ey = hy * fabsf(s.idy), ez = hz * fabsf(s.idz);
+  tn = fmaxf(fmaxf(mx - ex, my - ey), fmaxf(mz - ez, tmin32));
+  const float tf = fminf(fminf(mx + ex, my + ey), fminf(mz + ez, tbest32));
+#endif
+  hit = tn <= fmaf(fabsf(tf), 4e-6f, tf);
+}
+
+// ------------------------------------------------------------------------------------------------
 // closest surface hit: fp32 BVH2 cull + f64 leaves.  Replaces HittableList::hit / BvhNode::hit /
 // Aabb::hit (src/hittable.rs:88-109, 216-236, src/object.rs:340-370) with the build's own tree.
 // ------------------------------------------------------------------------------------------------
 template <bool STATS>
 RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& best, DStats* st) {
-  const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
-  const float idx = 1.0f / (float)r.dx, idy = 1.0f / (float)r.dy, idz = 1.0f / (float)r.dz;
+  const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, (float)r.dx, (float)r.dy, (float)r.dz);
   const float tmin32 = __double2float_rd(tmin);
   float tbest32 = __double2float_ru(best.t);
   int stack[BVH_STACK];
@@ -228,19 +271,10 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
       RTB_ASSERT(node < S.n_nodes);
       const float4* N = S.nodes + 4 * (size_t)node;
       const float4 n0 = RTB_LDG(N + 0), n1 = RTB_LDG(N + 1), n2 = RTB_LDG(N + 2), n3 = RTB_LDG(N + 3);
-      // fminf/fmaxf drop NaNs (0 * inf when the origin sits on a slab plane of a parallel ray)
-      float a0 = (n0.x - ox) * idx, a1 = (n0.y - ox) * idx;
-      float b0 = (n0.z - oy) * idy, b1 = (n0.w - oy) * idy;
-      float c0 = (n2.x - oz) * idz, c1 = (n2.y - oz) * idz;
-      const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-      const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-      a0 = (n1.x - ox) * idx; a1 = (n1.y - ox) * idx;
-      b0 = (n1.z - oy) * idy; b1 = (n1.w - oy) * idy;
-      c0 = (n2.z - oz) * idz; c1 = (n2.w - oz) * idz;
-      const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-      const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-      const bool h0 = tn0 <= fmaf(fabsf(tf0), 2e-6f, tf0);
-      const bool h1 = tn1 <= fmaf(fabsf(tf1), 2e-6f, tf1);
+      float tn0, tn1;
+      bool h0, h1;
+      slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
+      slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
       int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
       if (h0 && h1) {
         if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }

@@ -21,6 +21,7 @@
 // extend refills idle lanes, and shading runs sorted by class.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
   bool have = false, exhausted = false;
   int pos = -1;
   Ray r;
-  float idx = 0.f, idy = 0.f, idz = 0.f, oxi = 0.f, oyi = 0.f, ozi = 0.f, tbest32 = 0.f;
+  SlabRay sr = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float tbest32 = 0.f;
   const float tmin32 = __double2float_rd(0.0001);
   Hit best;
   hit_reset(best);
@@ -221,8 +223,7 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
             PathRec p;
             unpack_geom(a, b, c, p);
             r = to_ray(p);
-            idx = 1.0f / p.dx; idy = 1.0f / p.dy; idz = 1.0f / p.dz;
-            oxi = (float)r.ox * idx; oyi = (float)r.oy * idy; ozi = (float)r.oz * idz;
+            sr = slab_ray(p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
             hit_reset(best);
             tbest32 = __double2float_ru(best.t);
             sp = 0;
@@ -241,18 +242,10 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
       if (STATS) st_nodes++;
       const float4* N = S.nodes + 4 * (size_t)node;
       const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
-      float a0 = fmaf(n0.x, idx, -oxi), a1 = fmaf(n0.y, idx, -oxi);
-      float b0 = fmaf(n0.z, idy, -oyi), b1 = fmaf(n0.w, idy, -oyi);
-      float c0 = fmaf(n2.x, idz, -ozi), c1 = fmaf(n2.y, idz, -ozi);
-      const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-      const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-      a0 = fmaf(n1.x, idx, -oxi); a1 = fmaf(n1.y, idx, -oxi);
-      b0 = fmaf(n1.z, idy, -oyi); b1 = fmaf(n1.w, idy, -oyi);
-      c0 = fmaf(n2.z, idz, -ozi); c1 = fmaf(n2.w, idz, -ozi);
-      const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-      const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-      const bool h0 = tn0 <= fmaf(fabsf(tf0), 4e-6f, tf0);
-      const bool h1 = tn1 <= fmaf(fabsf(tf1), 4e-6f, tf1);
+      float tn0, tn1;
+      bool h0, h1;
+      slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
+      slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
       int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
       if (h0 && h1) {
         if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
@@ -380,7 +373,7 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
             PathRec p;
             unpack_geom(a, b, c, p);
             if (any_surface) {
-              const float ix = 1.0f / p.dx, iy = 1.0f / p.dy, iz = 1.0f / p.dz;
+              const float ix = safe_rcp(p.dx), iy = safe_rcp(p.dy), iz = safe_rcp(p.dz);
               W.ox[e] = p.ox; W.oy[e] = p.oy; W.oz[e] = p.oz;
               W.dx[e] = p.dx; W.dy[e] = p.dy; W.dz[e] = p.dz; W.time[e] = p.time;
               W.idx[e] = ix; W.idy[e] = iy; W.idz[e] = iz;
@@ -426,26 +419,17 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
       int* const stack = stacks + e * WF_POOL_STACK;
       int node = W.node[e], sp = W.sp[e];
       if (phase == ST_INNER) {
-        const float idx = W.idx[e], idy = W.idy[e], idz = W.idz[e];
-        const float oxi = W.oxi[e], oyi = W.oyi[e], ozi = W.ozi[e];
+        const SlabRay sr = {W.idx[e], W.idy[e], W.idz[e], W.oxi[e], W.oyi[e], W.ozi[e]};
         const float tbest32 = __double2float_ru(W.tbest[e]);
 #pragma unroll 1
         for (int step = 0; step < WF_POOL_CHUNK && node >= 0 && node != TRAV_DONE; step++) {
           if (STATS) st_nodes++;
           const float4* N = S.nodes + 4 * (size_t)node;
           const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
-          float a0 = fmaf(n0.x, idx, -oxi), a1 = fmaf(n0.y, idx, -oxi);
-          float b0 = fmaf(n0.z, idy, -oyi), b1 = fmaf(n0.w, idy, -oyi);
-          float c0 = fmaf(n2.x, idz, -ozi), c1 = fmaf(n2.y, idz, -ozi);
-          const float tn0 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-          const float tf0 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-          a0 = fmaf(n1.x, idx, -oxi); a1 = fmaf(n1.y, idx, -oxi);
-          b0 = fmaf(n1.z, idy, -oyi); b1 = fmaf(n1.w, idy, -oyi);
-          c0 = fmaf(n2.z, idz, -ozi); c1 = fmaf(n2.w, idz, -ozi);
-          const float tn1 = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
-          const float tf1 = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
-          const bool h0 = tn0 <= fmaf(fabsf(tf0), 4e-6f, tf0);
-          const bool h1 = tn1 <= fmaf(fabsf(tf1), 4e-6f, tf1);
+          float tn0, tn1;
+          bool h0, h1;
+          slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
+          slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
           int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
           if (h0 && h1) {
             if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
@@ -712,16 +696,14 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   const unsigned long long tiles = (unsigned long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
   const int occ = ctx.extend_blocks_per_sm[collect_stats ? 1 : 0] < 1 ? 1 : ctx.extend_blocks_per_sm[collect_stats ? 1 : 0];
   const int per_sm = env_int("RTB_WF_EXTEND_BLOCKS", (occ + K - 1) / K, 1, 32);
-  const unsigned extend_grid = (unsigned)(ctx.sms * per_sm);
+  const long long extend_grid_full = (long long)ctx.sms * per_sm;
   // pool extend: needs the stacks to fit WF_POOL_STACK; one sub-pipeline only (it owns the scratch)
   const bool use_pool = ctx.extend_kind == 1 && K == 1 && S.bvh_depth + 2 <= WF_POOL_STACK && ctx.sms <= 160;
   int pool_per_sm = ctx.pool_blocks_per_sm[collect_stats ? 1 : 0];
   pool_per_sm = env_int("RTB_WF_POOL_BLOCKS", pool_per_sm < 1 ? 1 : pool_per_sm, 1, WF_POOL_MAX_BLOCKS_PER_SM);
   if (pool_per_sm > WF_POOL_MAX_BLOCKS_PER_SM) pool_per_sm = WF_POOL_MAX_BLOCKS_PER_SM;
-  const unsigned pool_grid = (unsigned)(ctx.sms * pool_per_sm);
+  const long long pool_grid_full = (long long)ctx.sms * pool_per_sm;
   int* const pool_scratch = reinterpret_cast<int*>(static_cast<char*>(d_workspace) + workspace_bytes - pool_scratch_bytes(160));
-  const unsigned gen_blocks = (unsigned)((cap + 255) / 256);
-  const unsigned shade_blocks = (unsigned)((cap + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
 
   struct Sub { WFQueues Q; RayRec* in; RayRec* out; cudaStream_t st; long long s0; bool active; };
   Sub sub[WF_MAX_SUB];
@@ -748,13 +730,22 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   double stage_ms[3] = {0., 0., 0.};
   if (profile)
     for (auto& ev : pe) cudaEventCreate(&ev);
-  const int poll_every = profile ? 1 : 8;
+  int poll_every = profile ? 1 : 8;
   int n_active = K;
   long long iters = 0;
+  // Upper bound of the rays of the coming iterations, known to the host only at polls: while paths are
+  // still being started the queue is full; once every path has started it can only shrink, so the last
+  // polled count bounds all later iterations and the launches of the decaying tail are sized to it.
+  long long bound[WF_MAX_SUB];
+  for (int k = 0; k < K; k++) bound[k] = cap;
   for (long long iter = 0; n_active > 0; iter++) {
     for (int k = 0; k < K; k++) {
       Sub& u = sub[k];
       if (!u.active) continue;
+      const unsigned gen_blocks = (unsigned)((bound[k] + 255) / 256);
+      const unsigned shade_blocks = (unsigned)((bound[k] + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
+      const unsigned extend_grid = (unsigned)std::min<long long>(extend_grid_full, (bound[k] + WF_EXTEND_BLOCK - 1) / WF_EXTEND_BLOCK);
+      const unsigned pool_grid = (unsigned)std::min<long long>(pool_grid_full, (bound[k] + 2 * WF_POOL_BLOCK - 1) / (2 * WF_POOL_BLOCK));
       // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue
       if (profile) cudaEventRecord(pe[0], u.st);
       k_wf_generate<<<gen_blocks, 256, 0, u.st>>>(S, u.Q, u.s0, u.out);
@@ -774,7 +765,10 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
       if (profile) {
         cudaEventRecord(pe[3], u.st);
         cudaEventSynchronize(pe[3]);
-        for (int j = 0; j < 3; j++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[j], pe[j + 1]); stage_ms[j] += ms; }
+        float it_ms[3];
+        for (int j = 0; j < 3; j++) { it_ms[j] = 0.f; cudaEventElapsedTime(&it_ms[j], pe[j], pe[j + 1]); stage_ms[j] += it_ms[j]; }
+        static const bool per_iter = getenv("RTB_WF_PROFILE") && atoi(getenv("RTB_WF_PROFILE")) >= 2;
+        if (per_iter) fprintf(stderr, "[rtb iter] %lld extend %.3f shade %.3f\n", iter, it_ms[1], it_ms[2]);
       }
       n_launch += 4;
     }
@@ -785,7 +779,14 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
       for (int k = 0; k < K; k++) {
         if (!sub[k].active) continue;
         if ((e = cudaStreamSynchronize(sub[k].st)) != cudaSuccess) return e;
-        if (h_c[k].next_path >= h_c[k].total_paths && h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
+        static const bool tail_sizing = env_int("RTB_WF_TAIL", 1, 0, 1) != 0;
+        if (h_c[k].next_path >= h_c[k].total_paths && !tail_sizing) {
+          if (h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
+        } else if (h_c[k].next_path >= h_c[k].total_paths) {
+          if (h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
+          bound[k] = std::max<long long>(h_c[k].n_out, 1);  // every path has started: the queue only shrinks
+          if (!profile) poll_every = bound[k] < cap / 4 ? 2 : 4;
+        }
       }
     }
   }

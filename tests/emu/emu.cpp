@@ -140,3 +140,42 @@ int emu_eval_light_pdf(void* p, const double* od, long long n, double* pdf) {
 }
 
 }  // extern "C"
+
+// diagnostic: per-segment node-visit counts over a render pass; records the rays whose traversal
+// visited more than `threshold` nodes (first `cap` of them) and returns how many there were.
+extern "C" long long emu_slow_rays(void* p, long long s_begin, long long s_end, int pixel_stride, unsigned long long threshold,
+                                   RtbRay* out, unsigned long long* out_visits, int cap, unsigned long long* histogram16) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  const int n = S.cam.width * S.cam.height;
+  long long found = 0;
+  for (int pixel = 0; pixel < n; pixel += pixel_stride)
+    for (long long s = s_begin; s < s_end; s++) {
+      PathState ps;
+      generate_primary(S, (uint32_t)pixel, (uint32_t)s, ps);
+      float Lr = 0, Lg = 0, Lb = 0;
+      bool alive = true;
+      while (alive) {
+        DStats st = {0, 0, 0, 0, 0, 0};
+        Event ev;
+        const Ray r = ps.ray;
+        extend<true>(S, ps, ev, &st);
+        int b = 0;
+        while ((1ull << b) < st.node_visits && b < 15) b++;
+        histogram16[b]++;
+        if (st.node_visits > threshold) {
+          if (found < cap) {
+            RtbRay& o = out[found];
+            o.origin[0] = r.ox; o.origin[1] = r.oy; o.origin[2] = r.oz;
+            o.direction[0] = r.dx; o.direction[1] = r.dy; o.direction[2] = r.dz;
+            o.time = r.time; o.t_min = 1e-4;
+            out_visits[found] = st.node_visits;
+          }
+          found++;
+        }
+        DStats dummy = {0, 0, 0, 0, 0, 0};
+        alive = shade(S, ps, ev, Lr, Lg, Lb, &dummy, false);
+      }
+    }
+  return found;
+}

@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
-for i in 1 2; do timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/b.log 2> gpurun_out/b.err; python -c "
-import json
-d=json.loads(open('gpurun_out/b.log').read().strip().splitlines()[-1]); print({k:round(d[k],2) for k in ('value','ms_per_step')}, 'e2e', round(d['e2e']['value'],1))"; grep e2e gpurun_out/b.err; done
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+for v in lohi new; do
+  if [ "$v" = "lohi" ]; then export RTB200_LIB=$PWD/surely_raytracing_b200/librtb200_lohi.so; else unset RTB200_LIB; fi
+  echo "== $v"; timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/b_$v.log 2> gpurun_out/b_$v.err; grep step_ms gpurun_out/b_$v.err
+  RTB_WF_PROFILE=1 timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_prof.log 2> gpurun_out/bench_prof.err; grep "rtb wavefront" gpurun_out/bench_prof.err | sed -n '2,2p'
+done
