@@ -2,8 +2,9 @@
 """bench.py -- Mpaths/s (camera samples/s) of the hot path on BASELINE.json's headline config:
 the book-2 final scene (c4) at 800x800, depth 40, on N B200s of one box.
 
-A "step" is one progressive pass per GPU: one row of the 100x100 stratum grid (100 strata for every
-one of the 640,000 pixels = 64 M paths per GPU per step).  Rows are dealt round-robin to the ranks
+A "step" is one progressive pass per GPU: one rtb_render call over 10 rows of the 100x100 stratum grid
+(1000 strata for every one of the 640,000 pixels = 640 M paths per GPU per step; --rows-per-step).
+Row blocks are dealt round-robin to the ranks
 (weak scaling: per-GPU work is fixed), each rank accumulates into its own fp32 buffer and ONE NCCL
 sum-reduce at the end of the timed region delivers the image to rank 0.
 
@@ -29,8 +30,9 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "c4"
 WORKLOAD_DESC = ("book-2 final scene (final_scene, reference src/main.rs:603-712) 800x800 depth 40, lights = empty "
-                 "(what main.rs passes); step = one 100-stratum row of the 10000-spp grid per GPU")
+                 "(what main.rs passes); step = 10 rows (1000 strata) of the 100x100 stratum grid per GPU")
 L2_FLUSH_BYTES = 256 << 20
+ROWS_PER_STEP = 10
 
 # Algorithmic lane-instruction constants per call (fp32-issue-slot equivalents; DFMA/DADD/DMUL = 2
 # slots on B200, whose FP64 pipe issues at half the FP32 rate).  Derived from the SASS of
@@ -48,6 +50,8 @@ def parse_args():
     ap.add_argument("--pipeline", default="default", choices=["default", "mega", "wavefront"])
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--width", type=int, default=0, help="override the image width (parity/debug only)")
+    ap.add_argument("--rows-per-step", type=int, default=ROWS_PER_STEP,
+                    help="rows of the sqrt x sqrt stratum grid rendered per step and GPU (one rtb_render call)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -208,7 +212,8 @@ def run_b200(args, rank, world, local_rank):
     info = scene.info
     W, H, sq = info.image_width, info.image_height, info.sqrt_spp
     n_px = W * H
-    paths_per_step_per_gpu = n_px * sq
+    R = max(1, min(args.rows_per_step, sq))
+    paths_per_step_per_gpu = n_px * sq * R
 
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -221,7 +226,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- warm-up -------------------------------------------------------------------------------
     for k in range(args.warmup):
-        lo, hi = pass_rows(k, world, rank, sq)
+        lo, hi = pass_rows(k, world, rank, sq, R)
         scene.render_device(accum.data_ptr(), lo, hi, stream=stream, pipeline=pipeline)
     torch.cuda.synchronize(dev)
     accum.zero_()
@@ -237,7 +242,7 @@ def run_b200(args, rank, world, local_rank):
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                                           # L2 flush, outside the step's events
-        lo, hi = pass_rows(args.warmup + k, world, rank, sq)
+        lo, hi = pass_rows(args.warmup + k, world, rank, sq, R)
         starts[k].record()
         scene.render_device(accum.data_ptr(), lo, hi, stream=stream, pipeline=pipeline)
         stops[k].record()
@@ -264,7 +269,7 @@ def run_b200(args, rank, world, local_rank):
     # sanity: the reduced image must hold exactly steps*world*sq samples per pixel
     if rank == 0:
         w_min, w_max = float(accum[..., 3].min()), float(accum[..., 3].max())
-        assert w_min == w_max == float(args.steps * world * sq), (w_min, w_max)
+        assert w_min == w_max == float(args.steps * world * sq * R), (w_min, w_max)
         assert bool(torch.isfinite(accum).all())
 
     # ---- e2e: host-buffer path, every step uploads the scene and reads the image back ------------------
@@ -273,16 +278,17 @@ def run_b200(args, rank, world, local_rank):
     d2h = n_px * 16
     host_px = np.zeros((H, W, 3), dtype=np.float64)
     e2e_steps = max(1, min(args.steps, 5))
-    for k in range(2):                                           # untimed warm-up of the host-buffer path
-        s2 = Scene(built, device=local_rank)                     # (first call allocates the cached workspace)
-        s2.render(0, 1, pipeline=pipeline, out=host_px)
+    for k in range(2):                                           # untimed warm-up of the host-buffer path: a call of the
+        s2 = Scene(built, device=local_rank)                     # timed size, so that the cached workspace (sized by the
+        lo, hi = pass_rows(k, world, rank, sq, R)                # call) is allocated before the timed region
+        s2.render(lo, hi, pipeline=pipeline, out=host_px)
         s2.close()
     host_px[:] = 0.0
     barrier()
     e0 = time.perf_counter()
     e2e_ms = []
     for k in range(e2e_steps):
-        lo, hi = pass_rows(args.warmup + k, world, rank, sq)
+        lo, hi = pass_rows(args.warmup + k, world, rank, sq, R)
         t_a = time.perf_counter()
         s2 = Scene(built, device=local_rank)                    # flatten + BVH build + H2D of the scene
         t_b = time.perf_counter()
@@ -342,7 +348,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 geometry / f32 shading", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC if args.workload == WORKLOAD else args.workload, "image": [W, H],
-                       "max_depth": info.max_depth, "paths_per_step_per_gpu": paths_per_step_per_gpu,
+                       "max_depth": info.max_depth, "paths_per_step_per_gpu": paths_per_step_per_gpu, "rows_per_step": R,
                        "pipeline": args.pipeline, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset)",
                        "scene_upload_ms": upload_ms, "surface_prims": info.n_surface_prims,
                        "bvh_nodes": info.n_bvh_nodes, "reduce_ms": reduce_ms, "wall_ms_timed_region": wall_ms},

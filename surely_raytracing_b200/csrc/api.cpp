@@ -159,7 +159,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   // (both leased from the process-wide cache), copied with a single cudaMemcpyAsync.
   {
     struct Part { const void* src; size_t bytes; size_t off; };
-    Part parts[11] = {
+    Part parts[13] = {
         {h.nodes.data(), h.nodes.size() * sizeof(float4), 0},
         {h.prims.data(), h.prims.size() * sizeof(double), 0},
         {h.prim_info.data(), h.prim_info.size() * sizeof(int4), 0},
@@ -171,6 +171,8 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
         {h.perlin_vec.data(), h.perlin_vec.size() * sizeof(float4), 0},
         {h.perlin_perm.data(), h.perlin_perm.size(), 0},
         {h.lights.data(), h.lights.size() * sizeof(DLight), 0},
+        {h.qnodes.data(), h.qnodes.size() * sizeof(uint4), 0},
+        {h.nodes4.data(), h.nodes4.size() * sizeof(float4), 0},
     };
     size_t total = 0;
     for (Part& p : parts) { p.off = total; total += (std::max<size_t>(p.bytes, 16) + 255) & ~(size_t)255; }
@@ -197,6 +199,8 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
     D.perlin_vec = reinterpret_cast<const float4*>(dp + parts[8].off);
     D.perlin_perm = reinterpret_cast<const uint8_t*>(dp + parts[9].off);
     D.lights = reinterpret_cast<const DLight*>(dp + parts[10].off);
+    D.qnodes = reinterpret_cast<const uint4*>(dp + parts[11].off);
+    D.nodes4 = reinterpret_cast<const float4*>(dp + parts[12].off);
     s->upload_bytes = total;
   }
   D.n_nodes = (int)h.nodes.size() / 4;
@@ -204,6 +208,11 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   D.n_prims = (int)h.prim_info.size();
   D.n_media = (int)h.media.size();
   D.n_lights = (int)h.lights.size();
+  for (int a = 0; a < 3; a++) { D.grid_base[a] = h.grid_base[a]; D.grid_inv_cell[a] = h.grid_inv_cell[a]; D.grid_cell[a] = h.grid_cell[a]; }
+  D.use_qnodes = h.use_qnodes;
+  D.use_bvh4 = h.use_bvh4;
+  D.n_materials = (int)h.materials.size();
+  D.n_textures = (int)h.textures.size();
   D.bvh_depth = h.bvh_depth;
   D.flags = h.flags;
   D.seed_lo = (uint32_t)h.seed;
@@ -249,13 +258,19 @@ static int check_range(const rtb_scene* s, const RtbRenderParams* p) {
   return RTB_OK;
 }
 
-// path slots in flight of the wavefront pipeline (RTB_WF_CAPACITY overrides, for tuning runs)
-static int64_t wavefront_capacity() {
-  static int64_t cap = [] {
+// Path slots in flight of the wavefront pipeline (RTB_WF_CAPACITY overrides, for tuning runs).
+// Every iteration pays ~55 us of launch gaps and kernel tails whatever the queue size, and the decaying
+// tail of a call (no new paths left to start) costs in proportion to it: measured on c4, 1/16 of the
+// call's paths is the sweet spot (64 M paths: 4 M slots; 512 M and more: 32 M slots = 4.6 GB of queues).
+static int64_t wavefront_capacity(int64_t total_paths) {
+  static const int64_t forced = [] {
     const char* e = getenv("RTB_WF_CAPACITY");
-    long long v = e ? atoll(e) : 0;
-    return (int64_t)(v >= 1024 ? v : (1 << 22));
+    const long long v = e ? atoll(e) : 0;
+    return (int64_t)(v >= 1024 ? v : 0);
   }();
+  if (forced) return forced;
+  int64_t cap = 1 << 20;
+  while (cap < (1 << 25) && cap * 16 < total_paths) cap <<= 1;
   return cap;
 }
 
@@ -268,7 +283,7 @@ static int render_into(rtb_scene* s, const RtbRenderParams* p, float4* d_accum, 
   CU(cudaEventRecord(s->ev0, stream));
   if (p->sample_end > p->sample_begin) {
     if (p->pipeline != RTB_PIPELINE_MEGAKERNEL) {  // default = wavefront
-      const int64_t cap = wavefront_capacity();
+      const int64_t cap = wavefront_capacity((int64_t)(p->sample_end - p->sample_begin) * s->host.cam.width * s->host.cam.height);
       const size_t ws = wavefront_workspace_bytes(s->dev, cap);
       CU(s->workspace.reserve(s->device, 2, ws, false));
       if (!s->wf_ready) {

@@ -3,9 +3,14 @@
 //
 //   nodes      float4[4*n_nodes]   BVH2, one 64 B record per inner node holding BOTH children's
 //                                  boxes (fp32, padded outward so the fp32 slab test is conservative)
+//   nodes4     float4[8*n_nodes4]  the same tree with every other level collapsed (BVH4, 128 B per node:
+//                                  lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] pad): half the
+//                                  dependent node steps per ray for the latency-bound wavefront extend
+//   qnodes     uint4[2*n_nodes]    the same tree in 32 B per node: child boxes as 16-bit cell indices
+//                                  of a scene-wide grid, rounded outward (one 32 B sector per visit)
 //   prims      double2[8*n_prims]  128 B per primitive in BVH-leaf order, f64, world space (instance
 //                                  transforms baked in); surfaces first, then medium-boundary prims
-//   prim_info  int4[n_prims]       {kind, material, xform, canonical id}
+//   prim_info  int4[n_prims]       {kind | flags | class << 16 | (material + 1) << 20, material, xform, canonical id}
 //   xforms     double2[n_xforms]   {cos, sin} of the composed rotate_y of an instance chain (uv only)
 //   media, materials, textures, texels (u8 RGB), perlin tables, lights: small tagged records.
 //
@@ -19,6 +24,7 @@
 #include <vector_types.h>
 #else
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 struct int4 { int x, y, z, w; };
 #endif
@@ -33,6 +39,10 @@ enum : int { PRIM_FLAG_MOVING = 0x100 };
 enum : int { CLS_MISS = 0, CLS_LIGHT = 1, CLS_LAMBERT_SOLID = 2, CLS_LAMBERT_TEX = 3, CLS_METAL = 4, CLS_DIELECTRIC = 5,
              CLS_ISOTROPIC = 6, CLS_NOISE = 7, NUM_CLASSES = 8 };
 constexpr int PRIM_CLASS_SHIFT = 16;
+// bits 20..31 of prim_info.x: material index + 1 (0 = does not fit, read prim_info.y), so that the one
+// word a hit record carries tells the shade stage kind, class and material without a gather
+constexpr int PRIM_MAT_SHIFT = 20;
+constexpr int PRIM_MAT_MAX = 4094;
 enum : int { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
 enum : int { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_IMAGE = 2, TEX_NOISE = 3 };
 enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
@@ -93,6 +103,8 @@ struct DCamera {
 
 struct DScene {
   const float4* nodes;
+  const uint4* qnodes;        // 2 per inner node: the same tree with 16-bit boxes (opt-in arm of wavefront extend)
+  const float4* nodes4;       // 8 per BVH4 node: every other level of the tree collapsed (wavefront extend)
   const double2* prims;
   const int4* prim_info;
   const double2* xforms;
@@ -104,9 +116,15 @@ struct DScene {
   const uint8_t* perlin_perm; // 768 per table: perm_x | perm_y | perm_z
   const DLight* lights;
   int n_nodes, n_surface_prims, n_prims, n_media, n_lights;
+  int n_materials, n_textures;
   int bvh_depth;
   uint32_t flags;
   uint32_t seed_lo, seed_hi;
+  double grid_base[3], grid_inv_cell[3];  // quantisation grid of qnodes: cell index = (x - base) * inv_cell
+  float grid_cell[3];
+  int use_qnodes;  // wavefront extend traverses qnodes (else nodes)
+  int use_bvh4;    // wavefront extend traverses nodes4
+  int pad2;
   DCamera cam;
 };
 

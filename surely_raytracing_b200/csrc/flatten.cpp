@@ -341,7 +341,8 @@ int shading_class(const RtbSceneDesc& d, int material) {
 
 void emit_prim(const RtbSceneDesc& d, HostScene& out, const Baked& b) {
   out.prims.insert(out.prims.end(), b.payload, b.payload + PRIM_DOUBLES);
-  out.prim_info.push_back(int4{b.kind | b.flags | (shading_class(d, b.material) << PRIM_CLASS_SHIFT), b.material, b.xform, b.id});
+  const int mat_bits = (b.material >= 0 && b.material <= PRIM_MAT_MAX) ? ((b.material + 1) << PRIM_MAT_SHIFT) : 0;
+  out.prim_info.push_back(int4{b.kind | b.flags | (shading_class(d, b.material) << PRIM_CLASS_SHIFT) | mat_bits, b.material, b.xform, b.id});
 }
 
 bool texture_needs_uv(const RtbSceneDesc& d, int ti, int depth = 0) {
@@ -517,6 +518,48 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
   out.n_surface_prims = (int)B.surfaces.size();
 
+  // Quantisation grid of the 32-byte nodes: 16-bit cell indices over the padded root box, per axis.
+  // Child boxes are rounded outward and then widened by QPAD cells: the kernel evaluates
+  // t = (2^23 + k) * inv_d - (2^23 + o') * inv_d with the second product rounded to fp32, which moves
+  // every plane by at most 0.5 (1 + |o'| / 2^23) <= 1 cell for ray origins within 2^23 cells of the
+  // grid (beyond that the kernel traverses unculled).
+  constexpr int QPAD = 2;
+  if (!B.surfaces.empty()) {
+    const Box& rb = bvh.nodes[0].box;
+    for (int a = 0; a < 3; a++) {
+      const double lo = rb.lo[a] - pad, hi = rb.hi[a] + pad;
+      const double cell = std::max(hi - lo, 1e-9 * M) / 65500.;
+      out.grid_cell[a] = (float)cell;
+      out.grid_base[a] = lo - 16. * (double)out.grid_cell[a];
+      out.grid_inv_cell[a] = 1. / (double)out.grid_cell[a];
+    }
+  }
+  auto quant = [&](const Box& bx, int a) -> unsigned {
+    const double lo = (bx.lo[a] - pad - out.grid_base[a]) * out.grid_inv_cell[a];
+    const double hi = (bx.hi[a] + pad - out.grid_base[a]) * out.grid_inv_cell[a];
+    const long long klo = std::max<long long>(0, (long long)std::floor(lo) - QPAD);
+    const long long khi = std::min<long long>(65535, (long long)std::ceil(hi) + QPAD);
+    return (unsigned)klo | ((unsigned)khi << 16);
+  };
+  // expected-visit inflation of the grid boxes: sum of surface areas, quantised vs exact (SAH measure)
+  double sa_exact = 0., sa_quant = 0.;
+  auto emit_qnode = [&](int self, const Box& b0, const Box& b1, int ref0, int ref1) {
+    if (out.qnodes.size() < 2 * (size_t)(self + 1)) out.qnodes.resize(2 * (size_t)(self + 1));
+    const Box* bs[2] = {&b0, &b1};
+    const int refs2[2] = {ref0, ref1};
+    for (int c = 0; c < 2; c++) {
+      const unsigned q[3] = {quant(*bs[c], 0), quant(*bs[c], 1), quant(*bs[c], 2)};
+      out.qnodes[2 * (size_t)self + c] = uint4{q[0], q[1], q[2], (unsigned)refs2[c]};
+      double e[3], g[3];
+      for (int a = 0; a < 3; a++) {
+        e[a] = bs[c]->hi[a] - bs[c]->lo[a] + 2. * pad;
+        g[a] = (double)((q[a] >> 16) - (q[a] & 0xFFFFu)) * (double)out.grid_cell[a];
+      }
+      sa_exact += e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+      sa_quant += g[0] * g[1] + g[1] * g[2] + g[2] * g[0];
+    }
+  };
+
   // inner nodes get consecutive device indices in DFS order (root = 0)
   auto leaf_ref = [](int first, int count) { return ~((first << 3) | (count - 1)); };
   std::function<int(int)> emit_node = [&](int bi) -> int {
@@ -537,11 +580,13 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     std::memcpy(&r0, &refs[0], 4);
     std::memcpy(&r1, &refs[1], 4);
     N[3] = float4{r0, r1, 0.f, 0.f};
+    emit_qnode(self, *cb[0], *cb[1], refs[0], refs[1]);
     return self;
   };
   if (B.surfaces.empty()) {
     // no surfaces: the kernels skip traversal when n_surface_prims == 0; keep one inert node
     out.nodes = {float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}, float4{0.f, 0.f, 0.f, 0.f}};
+    out.qnodes = {uint4{0u, 0u, 0u, 0u}, uint4{0u, 0u, 0u, 0u}};
   } else if (bvh.nodes[0].left < 0) {
     // a single leaf: both children of the root reference it (the second test is a no-op by the
     // tie rule -- the reference's BvhNode::new duplicates a lone object the same way, hittable.rs:161-162)
@@ -554,10 +599,73 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     float r0;
     std::memcpy(&r0, &ref0, 4);
     out.nodes = {n0, n0, float4{lz, hz, lz, hz}, float4{r0, r0, 0.f, 0.f}};
+    emit_qnode(0, bx, bx, ref0, ref0);
   } else {
     emit_node(0);
   }
 
+  // Scenes whose primitives are tiny against the scene extent (book-1: 0.2-radius spheres on a
+  // 1000-radius ground) lose too much to the grid: those keep the 64-byte fp32 nodes.
+  // MEASURED on c4 (B200): 35.1 ms extend per step with the 32-byte nodes vs 34.2 ms with the fp32 nodes --
+  // the L1 wavefronts fall as intended, but the loop is bound by instruction issue and the 12 extra PRMT
+  // per visit cost more than the loads save.  Kept as an opt-in arm (RTB_QNODES=1) for scenes whose
+  // trees do not fit L1; the surface-area test still vetoes it where the grid is too coarse.
+  out.use_qnodes = 0;
+  if (const char* e = getenv("RTB_QNODES")) out.use_qnodes = (atoi(e) != 0 && !B.surfaces.empty() && sa_quant <= 1.03 * sa_exact) ? 1 : 0;
+  // ---- BVH4: collapse every other level of the emitted BVH2 (same fp32 boxes, so the cull is the same) ----
+  // A 4-wide node halves the dependent node steps per ray (c4: 12.6 -> 6.9 visits).
+#if !defined(RTB_SLAB_CENTER)
+  if (!B.surfaces.empty() && 3 * ((bvh.max_depth + 1) / 2) + 4 <= BVH_STACK) {
+    struct Child { float lo[3], hi[3]; int ref; };
+    auto child_of = [&](int node2, int c) {
+      const float4* N = &out.nodes[4 * (size_t)node2];
+      Child ch;
+      if (c == 0) { ch.lo[0] = N[0].x; ch.hi[0] = N[0].y; ch.lo[1] = N[0].z; ch.hi[1] = N[0].w; ch.lo[2] = N[2].x; ch.hi[2] = N[2].y; std::memcpy(&ch.ref, &N[3].x, 4); }
+      else { ch.lo[0] = N[1].x; ch.hi[0] = N[1].y; ch.lo[1] = N[1].z; ch.hi[1] = N[1].w; ch.lo[2] = N[2].z; ch.hi[2] = N[2].w; std::memcpy(&ch.ref, &N[3].y, 4); }
+      return ch;
+    };
+    std::function<int(int)> emit4 = [&](int node2) -> int {
+      const int self = (int)out.nodes4.size() / 8;
+      out.nodes4.resize(out.nodes4.size() + 8);
+      Child kids[4];
+      int nk = 0;
+      for (int c = 0; c < 2; c++) {
+        const Child ch = child_of(node2, c);
+        if (ch.ref >= 0) { kids[nk++] = child_of(ch.ref, 0); kids[nk++] = child_of(ch.ref, 1); }
+        else kids[nk++] = ch;
+      }
+      // a lone leaf under the root is referenced by both BVH2 children: keep one
+      if (nk == 2 && kids[0].ref < 0 && kids[0].ref == kids[1].ref) nk = 1;
+      float v[6][4];
+      int refs[4];
+      const float inf = std::numeric_limits<float>::infinity();
+      for (int k = 0; k < 4; k++) {
+        if (k < nk) {
+          for (int a = 0; a < 3; a++) { v[2 * a][k] = kids[k].lo[a]; v[2 * a + 1][k] = kids[k].hi[a]; }
+          refs[k] = kids[k].ref >= 0 ? emit4(kids[k].ref) : kids[k].ref;
+        } else {  // empty slot: both x planes at +inf -> the slab interval is empty for every ray
+          for (int j = 0; j < 6; j++) v[j][k] = 0.f;
+          v[0][k] = v[1][k] = inf;
+          refs[k] = 0;
+        }
+      }
+      float4* N = &out.nodes4[8 * (size_t)self];
+      for (int j = 0; j < 6; j++) N[j] = float4{v[j][0], v[j][1], v[j][2], v[j][3]};
+      float r[4];
+      std::memcpy(r, refs, 16);
+      N[6] = float4{r[0], r[1], r[2], r[3]};
+      N[7] = float4{0.f, 0.f, 0.f, 0.f};
+      return self;
+    };
+    emit4(0);
+    // MEASURED on c4 (B200, ncu in profiles/): visits per ray fall 12.3 -> 6.9, but a 128-byte node is seven
+    // load instructions per visit and the L1 data pipe -- already at 75 % with the BVH2 -- saturates
+    // (81 %, long-scoreboard stalls 4.5 -> 6.1 per issue): 555 vs 487 us per launch.  Opt-in (RTB_BVH4=1).
+    out.use_bvh4 = 0;
+    if (const char* e = getenv("RTB_BVH4")) out.use_bvh4 = atoi(e) != 0 ? 1 : 0;
+  }
+#endif
+  if (out.nodes4.empty()) out.nodes4.assign(8, float4{0.f, 0.f, 0.f, 0.f});
   lap("emit");
   // ---- media: boundary primitives after the surfaces, in DFS order ----------------------------------
   for (size_t mi = 0; mi < B.boundaries.size(); mi++) {

@@ -16,6 +16,12 @@ namespace rtb {
 
 struct HostScene {
   std::vector<float4> nodes;        // 4 per inner node
+  std::vector<uint4> qnodes;        // 2 per inner node (16-bit grid boxes), same indices as `nodes`
+  double grid_base[3] = {0., 0., 0.}, grid_inv_cell[3] = {1., 1., 1.};
+  float grid_cell[3] = {1.f, 1.f, 1.f};
+  std::vector<float4> nodes4;       // 8 per BVH4 node (collapsed from `nodes`)
+  int use_bvh4 = 0;
+  int use_qnodes = 0;               // the grid inflates the boxes by < 3 % (surface-area measure): extend uses qnodes
   std::vector<double> prims;        // PRIM_DOUBLES per primitive (BVH order; surfaces, then boundaries)
   std::vector<int4> prim_info;
   std::vector<double2> xforms;

@@ -44,6 +44,13 @@ static inline void sincospif(float x, float* s, float* c) { *s = sinf(3.14159265
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {  // PRMT, default mode
+  const uint64_t src = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((src >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return r;
+}
 #endif
 
 namespace rtb {
@@ -118,6 +125,19 @@ struct Ray {
   double dx, dy, dz;  // direction, not normalised (Q3); secondary directions are fp32-valued
   double time;        // f64 so that the parity harness sees the reference's centre(time) exactly
 };
+
+// The small tagged tables of a scene.  The wavefront shade kernel stages them in shared memory (a
+// dependent chain of global gathers per item otherwise); every other caller points at the scene's own.
+struct Tables {
+  const DMaterial* materials;
+  const DTexture* textures;
+  const DMedium* media;
+};
+RTB_DEV Tables scene_tables(const DScene& S) {
+  Tables T;
+  T.materials = S.materials; T.textures = S.textures; T.media = S.media;
+  return T;
+}
 
 // ------------------------------------------------------------------------------------------------
 // primitive tests, f64.  Upper bound CLOSED in both (the caller applies the reference's
@@ -254,6 +274,47 @@ RTB_DEV void slab_box(float cx, float hx, float cy, float hy, float cz, float hz
 }
 
 // ------------------------------------------------------------------------------------------------
+// 32-byte nodes (DScene::qnodes): the same BVH2 with child boxes as 16-bit cell indices of a scene-
+// wide grid (lo | hi << 16 per axis; 2 x uint4 = {x, y, z, child ref} per child).  Why: ncu on the
+// traversal shows the L1 data pipe at 75 % of its peak -- every load instruction of a warp costs one
+// wavefront per distinct 32 B sector, lanes sit on different nodes, and a 64-byte fp32 node takes 4
+// load instructions.  A 32-byte node takes 2 and fills exactly one sector.
+// Decode without integer conversion: PRMT places the 16-bit index k in the mantissa of 2^23
+// (0x4B00kkkk = 2^23 + k exactly), and t = (2^23 + k) * inv_d - (2^23 + o') * inv_d is ONE FFMA; the
+// rounded second product moves a plane by <= 1 cell, which the builder's outward padding of 2 cells
+// absorbs (flatten.cpp).  Rays whose origin is more than 2^23 cells from the grid traverse unculled.
+// ------------------------------------------------------------------------------------------------
+RTB_DEV SlabRay slab_ray_q(const DScene& S, double ox, double oy, double oz, float dx, float dy, float dz) {
+  SlabRay s;
+  const double gx = (ox - S.grid_base[0]) * S.grid_inv_cell[0];
+  const double gy = (oy - S.grid_base[1]) * S.grid_inv_cell[1];
+  const double gz = (oz - S.grid_base[2]) * S.grid_inv_cell[2];
+  s.idx = S.grid_cell[0] * safe_rcp(dx); s.idy = S.grid_cell[1] * safe_rcp(dy); s.idz = S.grid_cell[2] * safe_rcp(dz);
+  s.oxi = (float)((8388608.0 + gx) * (double)s.idx);
+  s.oyi = (float)((8388608.0 + gy) * (double)s.idy);
+  s.ozi = (float)((8388608.0 + gz) * (double)s.idz);
+  if (!(fabs(gx) <= 8388608.0 && fabs(gy) <= 8388608.0 && fabs(gz) <= 8388608.0)) {
+    // far outside the grid (or non-finite): NaN slab distances are dropped by fminf/fmaxf -> no culling
+    s.idx = s.idy = s.idz = __int_as_float(0x7FC00000);
+  }
+  return s;
+}
+
+RTB_DEV void slab_box_q(uint32_t qx, uint32_t qy, uint32_t qz, const SlabRay& s, float tmin32, float tbest32, float& tn,
+                        bool& hit) {
+  const uint32_t M = 0x4B000000u;  // 2^23
+  const float a0 = fmaf(__uint_as_float(__byte_perm(qx, M, 0x7610)), s.idx, -s.oxi);
+  const float a1 = fmaf(__uint_as_float(__byte_perm(qx, M, 0x7632)), s.idx, -s.oxi);
+  const float b0 = fmaf(__uint_as_float(__byte_perm(qy, M, 0x7610)), s.idy, -s.oyi);
+  const float b1 = fmaf(__uint_as_float(__byte_perm(qy, M, 0x7632)), s.idy, -s.oyi);
+  const float c0 = fmaf(__uint_as_float(__byte_perm(qz, M, 0x7610)), s.idz, -s.ozi);
+  const float c1 = fmaf(__uint_as_float(__byte_perm(qz, M, 0x7632)), s.idz, -s.ozi);
+  tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin32));
+  const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest32));
+  hit = tn <= fmaf(fabsf(tf), 4e-6f, tf);
+}
+
+// ------------------------------------------------------------------------------------------------
 // closest surface hit: fp32 BVH2 cull + f64 leaves.  Replaces HittableList::hit / BvhNode::hit /
 // Aabb::hit (src/hittable.rs:88-109, 216-236, src/object.rs:340-370) with the build's own tree.
 // ------------------------------------------------------------------------------------------------
@@ -358,8 +419,7 @@ RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, do
 }
 
 // returns the event parameter t (or +inf) for medium `mi`, given the closest surface so far
-RTB_DEV double medium_event(const DScene& S, int mi, const Ray& r, double tmin, double tmax, float U) {
-  const DMedium& m = S.media[mi];
+RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, double tmin, double tmax, float U) {
   const float log_u = logf(U);  // U = 0 -> -inf -> hit_distance +inf: no event
   {  // the shortcut below, first in fp32 with a wide margin (most rays leave here)
     const float len32 = sqrtf((float)r.dx * (float)r.dx + (float)r.dy * (float)r.dy + (float)r.dz * (float)r.dz);
@@ -393,9 +453,8 @@ RTB_DEV double medium_event(const DScene& S, int mi, const Ray& r, double tmin, 
 // direction).  Two conservative fp32 rejections -- the free-flight shortcut (fast log, wide margin)
 // and the boundary-box line cull -- run before anything is widened to f64; both only ever skip
 // events that medium_event itself would reject, so the two pipelines take identical decisions.
-RTB_DEV double medium_event_lazy(const DScene& S, int mi, double ox, double oy, double oz, float dx, float dy, float dz,
+RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, double oy, double oz, float dx, float dy, float dz,
                                  double time, double tmin, double tmax, float U) {
-  const DMedium& m = S.media[mi];
   {
 #if defined(__CUDACC__)
     const float fast_log = __logf(U);
@@ -420,7 +479,7 @@ RTB_DEV double medium_event_lazy(const DScene& S, int mi, double ox, double oy, 
   r.ox = ox; r.oy = oy; r.oz = oz;
   r.dx = (double)dx; r.dy = (double)dy; r.dz = (double)dz;
   r.time = time;
-  return medium_event(S, mi, r, tmin, tmax, U);
+  return medium_event(S, m, r, tmin, tmax, U);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,9 +521,9 @@ RTB_DEV float perlin_turb(const DScene& S, int table, double px, double py, doub
   return fabsf(accum);
 }
 
-RTB_DEV V3 texture_value(const DScene& S, int ti, float u, float v, double px, double py, double pz) {
+RTB_DEV V3 texture_value(const DScene& S, const DTexture* textures, int ti, float u, float v, double px, double py, double pz) {
   for (int guard = 0; guard < 16; guard++) {
-    const DTexture& t = S.textures[ti];
+    const DTexture& t = textures[ti];
     if (t.kind == TEX_SOLID) return v3(t.color[0], t.color[1], t.color[2]);  // texture.rs:44-46
     if (t.kind == TEX_CHECKER) {  // texture.rs:71-81 (Q19): floor in f64, Rust `%` keeps the sign
       const int x = (int)floor(t.scale * px), y = (int)floor(t.scale * py), z = (int)floor(t.scale * pz);
@@ -489,6 +548,9 @@ RTB_DEV V3 texture_value(const DScene& S, int ti, float u, float v, double px, d
     return v3(g, g, g);
   }
   return v3(0.f, 0.f, 0.f);
+}
+RTB_DEV V3 texture_value(const DScene& S, int ti, float u, float v, double px, double py, double pz) {
+  return texture_value(S, S.textures, ti, u, v, px, py, pz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,6 +727,7 @@ struct Event {
   int prim;   // >= 0 surface primitive (BVH order); -1 none
   int medium; // >= 0: the event is a scatter inside this medium
   int have_ab;  // quad planar coordinates a, b are valid (else shade recomputes them when a texture needs uv)
+  int info_x;   // prim_info[prim].x when the caller already has it (wavefront hit records carry it), else 0
 };
 
 // world.hit(r, Interval{0.0001, INF})  src/render.rs:264-270
@@ -673,22 +736,22 @@ RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st)
   Hit best;
   hit_reset(best);
   if (S.n_surface_prims > 0) closest_surface<STATS>(S, ps.ray, 0.0001, best, st);
-  ev.t = best.t; ev.a = best.a; ev.b = best.b; ev.prim = best.prim; ev.medium = -1; ev.have_ab = 1;
+  ev.t = best.t; ev.a = best.a; ev.b = best.b; ev.prim = best.prim; ev.medium = -1; ev.have_ab = 1; ev.info_x = 0;
   if (S.n_media > 0) {
     Rand4 u;
     for (int mi = 0; mi < S.n_media; mi++) {
       if ((mi & 3) == 0) u = rand4(S, ps.pixel, ps.sample, ps.bounce, 1u + (uint32_t)(mi >> 2));
       const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
       if (STATS) st->medium_probes++;
-      const double tm = medium_event(S, mi, ps.ray, 0.0001, ev.t, U);
+      const double tm = medium_event(S, S.media[mi], ps.ray, 0.0001, ev.t, U);
       if (tm < ev.t) { ev.t = tm; ev.medium = mi; ev.prim = -1; }
     }
   }
 }
 
 // material response at the event; returns false when the path ends (contribution added to L)
-RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb, DStats* st,
-                   bool stats) {
+RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb,
+                   DStats* st, bool stats) {
   const Ray& r = ps.ray;
   if (!(ev.t < RTB_INF)) {  // miss: cam.background  src/render.rs:298-309
     Lr += ps.bx * S.cam.background[0]; Lg += ps.by * S.cam.background[1]; Lb += ps.bz * S.cam.background[2];
@@ -701,13 +764,16 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
   int mat_id;
   if (ev.medium >= 0) {  // constant_medium.rs:82-90: arbitrary normal, front_face = true, u = v = 0
     n = v3(1.f, 0.f, 0.f);
-    mat_id = S.media[ev.medium].material;
+    mat_id = T.media[ev.medium].material;
   } else {
-    const int4 info = RTB_LDG(S.prim_info + ev.prim);
+    // kind | flags | class | material: from the hit record when it carries them, else one gather
+    int info_x = ev.info_x;
+    if (info_x == 0) info_x = RTB_LDG(S.prim_info + ev.prim).x;
     const double2* P = S.prims + (size_t)ev.prim * PRIM_D2;
-    mat_id = info.y;
-    const int needs_uv = S.materials[mat_id].needs_uv;
-    if ((info.x & 0xFF) == PRIM_QUAD) {
+    mat_id = (info_x >> PRIM_MAT_SHIFT) & 0xFFF;
+    mat_id = mat_id ? mat_id - 1 : RTB_LDG(S.prim_info + ev.prim).y;
+    const int needs_uv = T.materials[mat_id].needs_uv;
+    if ((info_x & 0xFF) == PRIM_QUAD) {
       const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
       front = ddot(r.dx, r.dy, r.dz, n01.x, n01.y, n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
       n = v3((float)n01.x, (float)n01.y, (float)n2d.x);
@@ -723,7 +789,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
     } else {
       const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
       double cx = c01.x, cy = c01.y, cz = c2r.x;
-      if (info.x & PRIM_FLAG_MOVING) {
+      if (info_x & PRIM_FLAG_MOVING) {
         const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
         cx += r.time * v01.x; cy += r.time * v01.y; cz += r.time * v2.x;
       }
@@ -732,7 +798,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
       front = (r.dx * nx + r.dy * ny + r.dz * nz) < 0.;
       n = v3((float)nx, (float)ny, (float)nz);
       if (needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105)
-        const double2 cs = RTB_LDG(S.xforms + info.z);
+        const double2 cs = RTB_LDG(S.xforms + RTB_LDG(S.prim_info + ev.prim).z);
         double u64, v64;
         sphere_uv(cs.x * nx - cs.y * nz, ny, cs.y * nx + cs.x * nz, u64, v64);
         tu = (float)u64; tv = (float)v64;
@@ -740,10 +806,10 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
     }
     if (!front) n = -n;
   }
-  const DMaterial& m = S.materials[mat_id];
+  const DMaterial& m = T.materials[mat_id];
   if (m.kind == MAT_DIFFUSE_LIGHT) {  // emitted: front face only; never scatters (Q16)  material.rs:210-221
     if (front) {
-      const V3 e = texture_value(S, m.texture, tu, tv, px, py, pz);
+      const V3 e = texture_value(S, T.textures, m.texture, tu, tv, px, py, pz);
       Lr += ps.bx * e.x; Lg += ps.by * e.y; Lb += ps.bz * e.z;
     }
     return false;
@@ -777,7 +843,7 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
   } else {
     // PdfPtr arm  src/render.rs:278-293: MixturePDF(HittablePDF(lights), material pdf)  pdf.rs:102-127
-    const V3 atten = texture_value(S, m.texture, tu, tv, px, py, pz);
+    const V3 atten = texture_value(S, T.textures, m.texture, tu, tv, px, py, pz);
     const bool lambert = m.kind == MAT_LAMBERTIAN;
     Onb uvw;
     if (lambert) uvw = onb_from_w(n);  // CosinePDF::new  pdf.rs:60-66
@@ -816,6 +882,10 @@ RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, f
   ps.ray.dx = (double)dir.x; ps.ray.dy = (double)dir.y; ps.ray.dz = (double)dir.z;
   ps.bounce++;
   return ps.bounce < (uint32_t)S.cam.max_depth;  // depth <= 0 -> (0,0,0)  src/render.rs:260-262
+}
+RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb, DStats* st,
+                   bool stats) {
+  return shade(S, scene_tables(S), ps, ev, Lr, Lg, Lb, st, stats);
 }
 
 }  // namespace rtb

@@ -10,11 +10,12 @@
 //                   survivors are appended (densely) to the next ray queue, finished paths accumulate
 //   k_wf_generate   tops the next queue up with new (pixel, stratum) rays      get_ray  render.rs:218-249
 //
-// Data layout in HBM (DESIGN.md "Queues"): two dense ray queues of 64-byte records (4 x 16 B: origin
-// f64x3 | direction f32x3, time | throughput f32x3, pixel | stratum, bounce) in QUEUE ORDER -- there
-// is no slot indirection, so extend and resolve stream them; one 16-byte hit record {t f64, id} per
-// queue position; per-class bins of queue positions for the shade stage.  All counters live on the
-// device; the host only polls "paths left" every few iterations.
+// Data layout in HBM (DESIGN.md "Queues"): two dense ray queues, each FOUR uint4 PLANES of `capacity`
+// entries (SoA of the 64-byte record: origin f64x3 | direction f32x3, time | throughput f32x3, pixel |
+// stratum, bounce) in QUEUE ORDER -- there is no slot indirection, every stage streams them and a
+// warp's 32 consecutive slots are 512 contiguous bytes per plane; one 16-byte hit record
+// {t f64, prim, prim_info.x} per queue position.  All counters live on the device; the host only polls
+// "paths left" every few iterations.
 //
 // Why this shape (ncu, profiles/r01_*): the megakernel keeps only 9.6 of 32 lanes active because
 // BVH trip counts differ per ray and lanes sit in different phases; here every kernel is one phase,
@@ -41,8 +42,8 @@ struct WFCounters {
   unsigned long long pad1;
 };
 
-struct RayRec { uint4 a, b, c, d; };  // 64 B, see pack/unpack
-struct alignas(16) HitRec { double t; int id; int pad; };
+struct RayRec { uint4 a, b, c, d; };  // the four words of one ray (see pack/unpack); stored as planes, see ray_plane
+struct alignas(16) HitRec { double t; int id; int info_x; };  // info_x = prim_info[id].x (0: miss)
 
 struct WFQueues {
   RayRec* rays_a;
@@ -88,6 +89,27 @@ __device__ __forceinline__ Ray to_ray(const PathRec& p) {
 }
 
 constexpr uint32_t PADDING_PIXEL = 0xFFFFFFFFu;  // inert lane of a border tile
+
+// A ray queue of `cap` slots is stored as FOUR PLANES of cap x 16 bytes (uint4 SoA: plane j holds word j
+// of every record), not as cap records of 64 bytes: the 32 consecutive slots a warp reads or writes are
+// then 512 contiguous bytes per plane (4 L1 wavefronts per instruction) instead of 32 sectors 64 bytes
+// apart (32 wavefronts) -- ncu had 77 % of the shade kernel's L1 wavefronts on these records.
+__device__ __forceinline__ const uint4* ray_plane(const RayRec* q, int cap, int j) {
+  return reinterpret_cast<const uint4*>(q) + (size_t)j * (size_t)cap;
+}
+__device__ __forceinline__ uint4* ray_plane(RayRec* q, int cap, int j) {
+  return reinterpret_cast<uint4*>(q) + (size_t)j * (size_t)cap;
+}
+
+// Queue records are streamed exactly once per kernel: load/store them with the evict-first policy so
+// that they do not push the BVH nodes and primitives (re-read by every ray) out of L1/L2.
+#if defined(RTB_NO_STREAM_HINTS)
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { *p = v; }
+#else
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { __stcs(p, v); }
+#endif
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -169,7 +191,10 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
   }
   p.sample = sample;
   p.bounce = 0u;
-  out[n_out + i] = pack(p);
+  const RayRec rec = pack(p);
+  const int o = n_out + i, cap = Q.capacity;
+  st_stream(ray_plane(out, cap, 0) + o, rec.a); st_stream(ray_plane(out, cap, 1) + o, rec.b);
+  st_stream(ray_plane(out, cap, 2) + o, rec.c); st_stream(ray_plane(out, cap, 3) + o, rec.d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -182,10 +207,21 @@ constexpr int WF_EXTEND_BLOCK = 128;
 #ifndef WF_EXTEND_MIN_BLOCKS
 #define WF_EXTEND_MIN_BLOCKS 7  // 72 regs, no spills; forcing 8 blocks (64 regs) spills and measured 4 % slower
 #endif
-constexpr int WF_FETCH_THRESHOLD = 28;  // refill when fewer than this many lanes hold a ray
+#ifndef WF_FETCH_THRESHOLD_N
+#define WF_FETCH_THRESHOLD_N 28
+#endif
+constexpr int WF_FETCH_THRESHOLD = WF_FETCH_THRESHOLD_N;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
+#ifndef WF_BREAK_LEFT
+#define WF_BREAK_LEFT 16  // measured on c4: 0 -> 35.1, 12 -> 33.9, 16 -> 33.4, 20 -> 33.5, 24 -> 33.8 ms extend per step
+#endif
 
-template <bool STATS>
+// NODES: which form of the tree is traversed, chosen per scene by the builder --
+//   NODES_BVH2  the 64-byte fp32 nodes;
+//   NODES_Q     the 32-byte quantised nodes (rtb_device.cuh, slab_box_q; opt-in, DScene::use_qnodes);
+//   NODES_BVH4  every other level collapsed (DScene::use_bvh4): half the dependent steps per ray.
+enum : int { NODES_BVH2 = 0, NODES_Q = 1, NODES_BVH4 = 2 };
+template <bool STATS, int NODES>
 __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
                                                                const RayRec* __restrict__ rays_in,
                                                                DStats* __restrict__ stats) {
@@ -195,13 +231,18 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
   unsigned long long st_nodes = 0, st_prims = 0;
   bool have = false, exhausted = false;
   int pos = -1;
-  Ray r;
+  // the ray waits for the f64 leaf tests as stored (f64 origin, fp32 direction and time): fewer live registers
+  double rox = 0., roy = 0., roz = 0.;
+  float rdx = 0.f, rdy = 0.f, rdz = 0.f, rtime = 0.f;
   SlabRay sr = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float tbest32 = 0.f;
   const float tmin32 = __double2float_rd(0.0001);
   Hit best;
   hit_reset(best);
   int stack[BVH_STACK];
+  // (A stale-entry cull -- stacking each subtree's entry distance and dropping entries beyond the best
+  // hit unvisited -- was measured: 0.4 fewer visits per ray, but the doubled stack traffic made it slower.)
+#define WF_POP() node = sp > 0 ? stack[--sp] : TRAV_DONE
   int sp = 0, node = TRAV_DONE, leaf = 0;  // leaf: postponed leaf reference (< 0) or 0
   const bool any_surface = S.n_surface_prims > 0;
   for (;;) {
@@ -218,12 +259,13 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
           const int k = base + __popc(need & ((1u << lane) - 1u));
           if (k < n) {
             pos = k;
-            const uint4* R = reinterpret_cast<const uint4*>(rays_in + k);
-            const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+            const uint4 a = ld_stream(ray_plane(rays_in, Q.capacity, 0) + k), b = ld_stream(ray_plane(rays_in, Q.capacity, 1) + k),
+                        c = ld_stream(ray_plane(rays_in, Q.capacity, 2) + k);
             PathRec p;
             unpack_geom(a, b, c, p);
-            r = to_ray(p);
-            sr = slab_ray(p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
+            rox = p.ox; roy = p.oy; roz = p.oz;
+            rdx = p.dx; rdy = p.dy; rdz = p.dz; rtime = p.time;
+            sr = NODES == NODES_Q ? slab_ray_q(S, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz) : slab_ray(p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
             hit_reset(best);
             tbest32 = __double2float_ru(best.t);
             sp = 0;
@@ -238,15 +280,54 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
     }
     if (!__any_sync(FULL, have)) break;
     // ---- inner nodes, speculative: keep descending after the first leaf is found -------------------
+#if WF_BREAK_LEFT > 0
+    const int entered = __popc(__ballot_sync(FULL, node >= 0 && node != TRAV_DONE));
+#endif
     while (node >= 0 && node != TRAV_DONE) {
       if (STATS) st_nodes++;
-      const float4* N = S.nodes + 4 * (size_t)node;
-      const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+      if (NODES == NODES_BVH4) {
+        const float4* N = S.nodes4 + 8 * (size_t)node;
+        const float4 lx = __ldg(N + 0), hx = __ldg(N + 1), ly = __ldg(N + 2), hy = __ldg(N + 3), lz = __ldg(N + 4), hz = __ldg(N + 5);
+        const int4 rf = __ldg(reinterpret_cast<const int4*>(N + 6));
+        float t0, t1, t2, t3;
+        bool h0, h1, h2, h3;
+        slab_box(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, sr, tmin32, tbest32, t0, h0);
+        slab_box(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, sr, tmin32, tbest32, t1, h1);
+        slab_box(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, sr, tmin32, tbest32, t2, h2);
+        slab_box(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, sr, tmin32, tbest32, t3, h3);
+        // nearest child next, the other hits are stacked in slot order (the warp model shows a full
+        // near-to-far sort buys < 1 % fewer visits)
+        const float inf = __int_as_float(0x7F800000);
+        const float k0 = h0 ? t0 : inf, k1 = h1 ? t1 : inf, k2 = h2 ? t2 : inf, k3 = h3 ? t3 : inf;
+        const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
+        if (h0 | h1 | h2 | h3) {
+          const bool n0 = h0 && k0 == kmin, n1 = !n0 && h1 && k1 == kmin, n2 = !(n0 | n1) && h2 && k2 == kmin;
+          const bool n3 = !(n0 | n1 | n2);
+          if (h0 && !n0) stack[sp++] = rf.x;
+          if (h1 && !n1) stack[sp++] = rf.y;
+          if (h2 && !n2) stack[sp++] = rf.z;
+          if (h3 && !n3) stack[sp++] = rf.w;
+          node = n0 ? rf.x : (n1 ? rf.y : (n2 ? rf.z : rf.w));
+        } else {
+          WF_POP();
+        }
+      } else {
       float tn0, tn1;
       bool h0, h1;
-      slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
-      slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
-      int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      int ch0, ch1;
+      if (NODES == NODES_Q) {
+        const uint4* N = S.qnodes + 2 * (size_t)node;
+        const uint4 q0 = __ldg(N + 0), q1 = __ldg(N + 1);
+        slab_box_q(q0.x, q0.y, q0.z, sr, tmin32, tbest32, tn0, h0);
+        slab_box_q(q1.x, q1.y, q1.z, sr, tmin32, tbest32, tn1, h1);
+        ch0 = (int)q0.w; ch1 = (int)q1.w;
+      } else {
+        const float4* N = S.nodes + 4 * (size_t)node;
+        const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+        slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
+        slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
+        ch0 = __float_as_int(n3.x); ch1 = __float_as_int(n3.y);
+      }
       if (h0 && h1) {
         if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
         stack[sp++] = ch1;
@@ -256,16 +337,26 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
       } else if (h1) {
         node = ch1;
       } else {
-        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+        WF_POP();
+      }
       }
       if (node < 0 && leaf == 0) {  // first leaf: postpone it and continue with the next node
         leaf = node;
-        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+        WF_POP();
       }
-      // every lane still in this loop holds a leaf already: stop speculating and test the leaves
-      if (!__any_sync(__activemask(), leaf == 0)) break;
+      // every lane still in this loop holds a leaf already: stop speculating and test the leaves.
+      // WF_BREAK_LEFT: also stop once that many lanes have dropped out of the loop (second leaf, or
+      // out of nodes) -- the warp model (tools/sim) puts the inner loop at 25 instead of 18 lanes.
+      const unsigned looping = __activemask();
+      if (!__any_sync(looping, leaf == 0)) break;
+#if WF_BREAK_LEFT > 0
+      if (entered - __popc(looping) >= WF_BREAK_LEFT) break;
+#endif
     }
     // ---- leaves: the postponed one, then the current node if it is a leaf too -------------------------
+    Ray r;
+    r.ox = rox; r.oy = roy; r.oz = roz;
+    r.dx = (double)rdx; r.dy = (double)rdy; r.dz = (double)rdz; r.time = (double)rtime;
     while (leaf < 0) {
       const int l = ~leaf;
       const int first = l >> 3, count = (l & 7) + 1;
@@ -276,14 +367,15 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
       leaf = 0;
       if (node < 0) {
         leaf = node;
-        node = sp > 0 ? stack[--sp] : TRAV_DONE;
+        WF_POP();
       }
     }
     if (have) tbest32 = __double2float_ru(best.t);
     if (have && node == TRAV_DONE) {
-      HitRec h;
-      h.t = best.t; h.id = best.prim; h.pad = 0;
-      Q.hits[pos] = h;
+      uint4 h;  // {t, prim, prim_info.x}: kind | flags | class | material travel with the hit
+      h.x = (unsigned)__double2loint(best.t); h.y = (unsigned)__double2hiint(best.t);
+      h.z = (unsigned)best.prim; h.w = best.prim >= 0 ? (unsigned)__ldg(&S.prim_info[best.prim].x) : 0u;
+      st_stream(reinterpret_cast<uint4*>(Q.hits + pos), h);
       have = false;
     }
   }
@@ -368,8 +460,8 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
           const int k = base + (half == 0 ? __popc(e0 & lt) : __popc(e0) + __popc(e1 & lt));
           if (mine && k < n) {
             const int e = lane + 32 * half;
-            const uint4* R = reinterpret_cast<const uint4*>(rays_in + k);
-            const uint4 a = __ldg(R + 0), b = __ldg(R + 1), c = __ldg(R + 2);
+            const uint4 a = __ldg(ray_plane(rays_in, Q.capacity, 0) + k), b = __ldg(ray_plane(rays_in, Q.capacity, 1) + k),
+                        c = __ldg(ray_plane(rays_in, Q.capacity, 2) + k);
             PathRec p;
             unpack_geom(a, b, c, p);
             if (any_surface) {
@@ -384,7 +476,7 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
               W.status[e] = ST_INNER;
             } else {  // nothing to traverse: record the miss
               HitRec h;
-              h.t = RTB_INF; h.id = -1; h.pad = 0;
+              h.t = RTB_INF; h.id = -1; h.info_x = 0;
               Q.hits[k] = h;
             }
           }
@@ -464,7 +556,8 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
       // ---- write the entry back / retire it -------------------------------------------------------------------
       if (node == TRAV_DONE) {
         HitRec h;
-        h.t = W.tbest[e]; h.id = W.best_prim[e]; h.pad = 0;
+        h.t = W.tbest[e]; h.id = W.best_prim[e];
+        h.info_x = h.id >= 0 ? __ldg(&S.prim_info[h.id].x) : 0;
         Q.hits[W.pos[e]] = h;
         W.status[e] = ST_EMPTY;
       } else {
@@ -492,10 +585,10 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
 // No global bins, no gathers: every global access of this kernel is sequential.
 // ------------------------------------------------------------------------------------------------
 #ifndef WF_SHADE_BLOCK_DIM
-#define WF_SHADE_BLOCK_DIM 256
+#define WF_SHADE_BLOCK_DIM 128  // measured on c4: 128 -> 23.0, 256 -> 23.9, 512 -> 26.0 ms shade per step
 #endif
 #ifndef WF_SHADE_MIN_BLOCKS
-#define WF_SHADE_MIN_BLOCKS 3
+#define WF_SHADE_MIN_BLOCKS 6
 #endif
 constexpr int WF_SHADE_BLOCK = WF_SHADE_BLOCK_DIM;
 constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
@@ -504,8 +597,15 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
   uint4 a, b, c, d;
   double t;
   int id;
-  int cls;
+  int info_x;  // prim_info[id].x of a surface hit (kind | flags | class | material)
 };
+constexpr int WF_SMEM_MATERIALS = 32, WF_SMEM_TEXTURES = 32, WF_SMEM_MEDIA = 4;
+#ifndef WF_SHADE_TABLES_SMEM
+#define WF_SHADE_TABLES_SMEM 0  // measured on c4: staging the tables costs 1.8 ms / step (generic loads + a barrier)
+#endif
+#ifndef WF_SHADE_MATCH_SORT
+#define WF_SHADE_MATCH_SORT 1
+#endif
 
 template <bool STATS>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
@@ -514,22 +614,59 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
                                                             DStats* __restrict__ stats) {
   const unsigned FULL = 0xFFFFFFFFu;
   __shared__ ShadeItem items[WF_SHADE_BLOCK];
+#if WF_SHADE_MATCH_SORT
+  __shared__ int class_count[NUM_CLASSES];
+#else
   __shared__ int warp_count[NUM_CLASSES][WF_SHADE_WARPS];  // [cls][warp]
   __shared__ int class_base[NUM_CLASSES];
+#endif
+#if WF_SHADE_TABLES_SMEM
+  __shared__ DMaterial s_materials[WF_SMEM_MATERIALS];
+  __shared__ DTexture s_textures[WF_SMEM_TEXTURES];
+  __shared__ DMedium s_media[WF_SMEM_MEDIA];
+#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = blockIdx.x * WF_SHADE_BLOCK + tid;
   const int n = Q.c->n_in;
   if (blockIdx.x * WF_SHADE_BLOCK >= n) return;  // whole block idle (uniform)
+  // ---- 0. stage the small scene tables in shared memory (else: a chain of dependent global gathers per item)
+  Tables T = scene_tables(S);
+#if WF_SHADE_TABLES_SMEM
+  if (S.n_materials <= WF_SMEM_MATERIALS && S.n_textures <= WF_SMEM_TEXTURES && S.n_media <= WF_SMEM_MEDIA) {
+    const int wm = S.n_materials * (int)(sizeof(DMaterial) / 4), wt = S.n_textures * (int)(sizeof(DTexture) / 4),
+              wd = S.n_media * (int)(sizeof(DMedium) / 4);
+    const int* gm = reinterpret_cast<const int*>(S.materials);
+    const int* gt = reinterpret_cast<const int*>(S.textures);
+    const int* gd = reinterpret_cast<const int*>(S.media);
+    for (int k = tid; k < wm; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_materials)[k] = __ldg(gm + k);
+    for (int k = tid; k < wt; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_textures)[k] = __ldg(gt + k);
+    for (int k = tid; k < wd; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_media)[k] = __ldg(gd + k);
+    T.materials = s_materials; T.textures = s_textures; T.media = s_media;
+  }
+#endif
+#if WF_SHADE_MATCH_SORT
+  if (tid < NUM_CLASSES) class_count[tid] = 0;
+#endif
   // ---- 1. load + medium events + class -----------------------------------------------------------
   ShadeItem it;
-  it.cls = -1;
+  int cls = -1;
   if (i < n) {
-    const uint4* R = reinterpret_cast<const uint4*>(rays_in + i);
-    it.a = __ldg(R + 0); it.b = __ldg(R + 1); it.c = __ldg(R + 2); it.d = __ldg(R + 3);
-    const HitRec h = Q.hits[i];
-    it.t = h.t; it.id = h.id;
+    const int cap = Q.capacity;
+    it.a = ld_stream(ray_plane(rays_in, cap, 0) + i); it.b = ld_stream(ray_plane(rays_in, cap, 1) + i);
+    it.c = ld_stream(ray_plane(rays_in, cap, 2) + i); it.d = ld_stream(ray_plane(rays_in, cap, 3) + i);
+    const uint4 h = ld_stream(reinterpret_cast<const uint4*>(Q.hits + i));
+    it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
+#if defined(WF_SHADE_PREFETCH)
+    // the shading lane (same SM, after the sort) gathers this primitive: start the fetch now
+    if (it.id >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.prims + (size_t)it.id * PRIM_D2));
+#endif
+  }
+#if WF_SHADE_TABLES_SMEM || WF_SHADE_MATCH_SORT
+  __syncthreads();  // tables staged, counters zeroed
+#endif
+  if (i < n) {
     if (it.d.y == PADDING_PIXEL) {
-      it.cls = CLS_MISS;
+      cls = CLS_MISS;
     } else {
       if (S.n_media > 0) {
         PathRec p;
@@ -539,22 +676,43 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
         for (int mi = 0; mi < S.n_media; mi++) {
           if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
           const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-          const double tm = medium_event_lazy(S, mi, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
+          const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
           if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
         }
       }
-      it.cls = it.id == -1 ? CLS_MISS
-                           : (it.id >= 0 ? ((__ldg(S.prim_info + it.id).x >> PRIM_CLASS_SHIFT) & 0xF)
-                                         : (S.media[-2 - it.id].cls_fast & 0xF));
+      cls = it.id == -1 ? CLS_MISS
+                        : (it.id >= 0 ? ((it.info_x >> PRIM_CLASS_SHIFT) & 0xF) : (T.media[-2 - it.id].cls_fast & 0xF));
     }
   }
-  // ---- 2. block-local counting sort by class -------------------------------------------------------
+  // ---- 2. block-local counting sort by class: one shared-memory atomic per (warp, class present) ----------
+#if defined(WF_SHADE_NO_SORT)
+  if (cls >= 0) items[tid] = it;  // A/B arm: no class sort
+  __syncthreads();
+#elif WF_SHADE_MATCH_SORT
+  int dst = 0;
+  {
+    const unsigned peers = __match_any_sync(FULL, cls);
+    int warp_base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (cls >= 0 && lane == leader) warp_base = atomicAdd(&class_count[cls], __popc(peers));
+    warp_base = __shfl_sync(FULL, warp_base, leader);
+    dst = warp_base + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (cls >= 0) {
+#pragma unroll
+    for (int k = 0; k < NUM_CLASSES - 1; k++)
+      if (k < cls) dst += class_count[k];
+    items[dst] = it;
+  }
+  __syncthreads();
+#else
   int rank_in_warp = 0;
 #pragma unroll
   for (int k = 0; k < NUM_CLASSES; k++) {
-    const unsigned m = __ballot_sync(FULL, it.cls == k);
+    const unsigned m = __ballot_sync(FULL, cls == k);
     if (lane == 0) warp_count[k][warp] = __popc(m);
-    if (it.cls == k) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+    if (cls == k) rank_in_warp = __popc(m & ((1u << lane) - 1u));
   }
   __syncthreads();
   if (tid < NUM_CLASSES) {  // exclusive prefix over classes (8 x 8 counters: one thread per class is enough)
@@ -564,12 +722,13 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     class_base[tid] = total_before;
   }
   __syncthreads();
-  if (it.cls >= 0) {
-    int dst = class_base[it.cls] + rank_in_warp;
-    for (int w = 0; w < warp; w++) dst += warp_count[it.cls][w];
+  if (cls >= 0) {
+    int dst = class_base[cls] + rank_in_warp;
+    for (int w = 0; w < warp; w++) dst += warp_count[cls][w];
     items[dst] = it;
   }
   __syncthreads();
+#endif
   const int n_block = min(WF_SHADE_BLOCK, n - blockIdx.x * WF_SHADE_BLOCK);
   // ---- 3. shade the item at sorted position `tid` -----------------------------------------------------
   bool alive = false;
@@ -589,8 +748,9 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
       ev.t = me.t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
       ev.prim = me.id >= 0 ? me.id : -1;
       ev.medium = me.id <= -2 ? -2 - me.id : -1;
+      ev.info_x = me.id >= 0 ? me.info_x : 0;
       float Lr = 0.f, Lg = 0.f, Lb = 0.f;
-      alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);
+      alive = shade(S, T, ps, ev, Lr, Lg, Lb, &st, STATS);
       if (alive) {
         p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
         p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
@@ -619,7 +779,11 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     int base = 0;
     if (lane == leader) base = atomicAdd(&Q.c->n_out, __popc(m));
     base = __shfl_sync(FULL, base, leader);
-    if (alive) rays_out[base + __popc(m & ((1u << lane) - 1u))] = out;
+    if (alive) {
+      const int o = base + __popc(m & ((1u << lane) - 1u)), cap = Q.capacity;
+      st_stream(ray_plane(rays_out, cap, 0) + o, out.a); st_stream(ray_plane(rays_out, cap, 1) + o, out.b);
+      st_stream(ray_plane(rays_out, cap, 2) + o, out.c); st_stream(ray_plane(rays_out, cap, 3) + o, out.d);
+    }
   }
   if (STATS) {
     if (st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
@@ -653,8 +817,17 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
   ctx->sms = 148;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, dev);
   ctx->extend_blocks_per_sm[0] = ctx->extend_blocks_per_sm[1] = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[0], k_wf_extend<false>, WF_EXTEND_BLOCK, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[1], k_wf_extend<true>, WF_EXTEND_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[0], k_wf_extend<false, NODES_BVH2>, WF_EXTEND_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extend_blocks_per_sm[1], k_wf_extend<true, NODES_BVH2>, WF_EXTEND_BLOCK, 0);
+  {  // the other node-format instantiations may differ by a few registers: take the smallest residency
+    int r[4] = {0, 0, 0, 0};
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[0], k_wf_extend<false, NODES_Q>, WF_EXTEND_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[1], k_wf_extend<true, NODES_Q>, WF_EXTEND_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[2], k_wf_extend<false, NODES_BVH4>, WF_EXTEND_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[3], k_wf_extend<true, NODES_BVH4>, WF_EXTEND_BLOCK, 0);
+    for (int k = 0; k < 4; k++)
+      if (r[k] > 0 && r[k] < ctx->extend_blocks_per_sm[k & 1]) ctx->extend_blocks_per_sm[k & 1] = r[k];
+  }
   ctx->pool_blocks_per_sm[0] = ctx->pool_blocks_per_sm[1] = 4;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[0], k_wf_extend_pool<false>, WF_POOL_BLOCK, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[1], k_wf_extend_pool<true>, WF_POOL_BLOCK, 0);
@@ -756,8 +929,16 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         if (collect_stats) k_wf_extend_pool<true><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
         else k_wf_extend_pool<false><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
       } else {
-        if (collect_stats) k_wf_extend<true><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
-        else k_wf_extend<false><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        if (S.use_qnodes) {
+          if (collect_stats) k_wf_extend<true, NODES_Q><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+          else k_wf_extend<false, NODES_Q><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        } else if (S.use_bvh4) {
+          if (collect_stats) k_wf_extend<true, NODES_BVH4><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+          else k_wf_extend<false, NODES_BVH4><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        } else {
+          if (collect_stats) k_wf_extend<true, NODES_BVH2><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+          else k_wf_extend<false, NODES_BVH2><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        }
       }
       if (profile) cudaEventRecord(pe[2], u.st);
       if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);

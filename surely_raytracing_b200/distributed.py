@@ -14,11 +14,13 @@ def split_samples(spp: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def pass_rows(step: int, world: int, rank: int, sqrt_spp: int) -> tuple[int, int]:
-    """bench.py's progressive passes: pass `step` of rank `rank` is one row s_j of the sqrt x sqrt stratum
-    grid (sqrt_spp strata); rows are dealt round-robin over ranks and wrap around the grid."""
-    row = (step * world + rank) % sqrt_spp
-    return row * sqrt_spp, (row + 1) * sqrt_spp
+def pass_rows(step: int, world: int, rank: int, sqrt_spp: int, rows: int = 1) -> tuple[int, int]:
+    """bench.py's progressive passes: pass `step` of rank `rank` is a block of `rows` consecutive rows s_j
+    of the sqrt x sqrt stratum grid (rows * sqrt_spp strata); blocks are dealt round-robin over ranks and
+    wrap around the grid."""
+    rows = max(1, min(rows, sqrt_spp))
+    block = (step * world + rank) % (sqrt_spp // rows)
+    return block * rows * sqrt_spp, (block + 1) * rows * sqrt_spp
 
 
 def reduce_to_root(accum, root: int = 0):

@@ -38,6 +38,10 @@ void* emu_scene_create(const RtbSceneDesc* d) {
   D.perlin_vec = h.perlin_vec.data(); D.perlin_perm = h.perlin_perm.data(); D.lights = h.lights.data();
   D.n_nodes = (int)h.nodes.size() / 4; D.n_surface_prims = h.n_surface_prims; D.n_prims = (int)h.prim_info.size();
   D.n_media = (int)h.media.size(); D.n_lights = (int)h.lights.size(); D.bvh_depth = h.bvh_depth;
+  D.n_materials = (int)h.materials.size(); D.n_textures = (int)h.textures.size();
+  D.qnodes = h.qnodes.data(); D.use_qnodes = h.use_qnodes;
+  D.nodes4 = h.nodes4.data(); D.use_bvh4 = h.use_bvh4;
+  for (int a = 0; a < 3; a++) { D.grid_base[a] = h.grid_base[a]; D.grid_inv_cell[a] = h.grid_inv_cell[a]; D.grid_cell[a] = h.grid_cell[a]; }
   D.flags = h.flags; D.seed_lo = (uint32_t)h.seed; D.seed_hi = (uint32_t)(h.seed >> 32);
   D.cam = h.cam;
   return e;
