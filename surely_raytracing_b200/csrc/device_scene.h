@@ -48,7 +48,20 @@ enum : int { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_IMAGE = 2, TEX_NOISE = 3 };
 enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
 
 constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
-constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf (leaf ref = ~((first << 3) | (count - 1)))
+constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf
+// Leaf reference (negative child index): ~(first << 5 | moving << 4 | quad << 3 | count - 1).  The two kind
+// bits describe the leaf's primitive when count == 1 (the builder's default), so the traversal can run
+// its test without touching prim_info -- one L1 wavefront less per test on a saturated L1 data pipe.
+constexpr int LEAF_KIND_QUAD = 1, LEAF_KIND_MOVING = 2;
+#if defined(__CUDACC__)
+#define RTB_HD __host__ __device__ inline
+#else
+#define RTB_HD inline
+#endif
+RTB_HD int leaf_make(int first, int count, int kind_bits) { return ~((first << 5) | (kind_bits << 3) | (count - 1)); }
+RTB_HD int leaf_first(int ref) { return (~ref) >> 5; }
+RTB_HD int leaf_count(int ref) { return ((~ref) & 7) + 1; }
+RTB_HD int leaf_kind_bits(int ref) { return ((~ref) >> 3) & 3; }
 
 // primitive payload, 16 doubles (8 x double2 = 128 B), the fields of the reference structs:
 //   SPHERE: cx cy | cz r | cvx cvy | cvz - | ...                 (center(t) = c + t * cv, src/object.rs:74-80)
@@ -84,14 +97,14 @@ struct DMedium {
   float pad;
 };
 
-struct alignas(16) DLight {
-  double prim[16];  // same payload as `prims` (world space, time 0); first + 16-aligned: read as double2
+struct alignas(32) DLight {
+  double prim[16];  // same payload as `prims` (world space, time 0); first + 32-aligned: read as double2 pairs
   double q[3], u[3], v[3];  // QUAD: sampling frame
   double area;
   int kind;
   int pad;
 };
-static_assert(sizeof(DLight) % 16 == 0, "DLight records must keep prim[] 16-byte aligned");
+static_assert(sizeof(DLight) % 32 == 0, "DLight records must keep prim[] 32-byte aligned (256-bit loads)");
 
 struct DCamera {
   double center[3], pixel00[3], du[3], dv[3], disk_u[3], disk_v[3];

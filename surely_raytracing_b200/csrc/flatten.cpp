@@ -561,7 +561,11 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   };
 
   // inner nodes get consecutive device indices in DFS order (root = 0)
-  auto leaf_ref = [](int first, int count) { return ~((first << 3) | (count - 1)); };
+  auto leaf_ref = [&](int first, int count) {
+    const Baked& b0 = B.surfaces[bvh.order[first]];
+    const int bits = (b0.kind == PRIM_QUAD ? LEAF_KIND_QUAD : 0) | ((b0.flags & PRIM_FLAG_MOVING) ? LEAF_KIND_MOVING : 0);
+    return leaf_make(first, count, bits);
+  };
   std::function<int(int)> emit_node = [&](int bi) -> int {
     const BuildNode& bn = bvh.nodes[bi];
     if (bn.left < 0) return leaf_ref(bn.first, bn.count);

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) k_trace_complete(const __grid_constant__ 
   const Ray r = load_ray(rays[i]);
   const TraceHit h = closest[i];
   Hit best;
-  best.t = h.t; best.a = h.a; best.b = h.b; best.prim = h.prim; best.kind = -1; best.id = -1;
+  best.t = h.t; best.a = h.a; best.b = h.b; best.prim = h.prim;
   RtbHit out;
   complete_hit(S, r, best, out);
   hits[i] = out;

@@ -145,9 +145,11 @@ RTB_DEV Tables scene_tables(const DScene& S) {
 // (Interval::surrounds) -- src/object.rs:161-163, 462, src/interval.rs:21-27 (Q4).
 // ------------------------------------------------------------------------------------------------
 // Quad::hit  src/object.rs:453-490, operation by operation (payload: normal d | q | u | v | w)
-RTB_DEV bool quad_test(const double2* __restrict__ P, const Ray& r, double tmin, double tmax, double& t_out,
-                       double& a_out, double& b_out) {
-  const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
+RTB_DEV bool quad_test(const double2* __restrict__ P, const double2 n01, const double2 n2d, const Ray& r, double tmin,
+                       double tmax, double& t_out, double& a_out, double& b_out) {
+  // n01, n2d = P[0], P[1], loaded by the caller (test_prim issues them together with prim_info)
+  // (256-bit loads of the payload -- one instruction per 32-byte sector, as the node loads of the wavefront
+  // traversal use -- were measured here too: 1 % slower, the wider destination costs two registers.)
   const double denom = ddot(n01.x, n01.y, n2d.x, r.dx, r.dy, r.dz);
   if (fabs(denom) < 1e-8) return false;
   const double t = dsub(n2d.y, ddot(n01.x, n01.y, n2d.x, r.ox, r.oy, r.oz)) / denom;
@@ -171,12 +173,15 @@ RTB_DEV bool quad_test(const double2* __restrict__ P, const Ray& r, double tmin,
   t_out = t; a_out = a; b_out = b;
   return true;
 }
+RTB_DEV bool quad_test(const double2* __restrict__ P, const Ray& r, double tmin, double tmax, double& t_out,
+                       double& a_out, double& b_out) {
+  return quad_test(P, RTB_LDG(P + 0), RTB_LDG(P + 1), r, tmin, tmax, t_out, a_out, b_out);
+}
 
 // Sphere::hit  src/object.rs:145-166, operation by operation (root selection only; normal/uv are
 // completed for the winner).  payload: cx cy | cz r | cvx cvy | cvz -
-RTB_DEV bool sphere_test(const double2* __restrict__ P, int moving, const Ray& r, double time, double tmin, double tmax,
-                         double& t_out) {
-  const double2 c01 = RTB_LDG(P + 0), c2r = RTB_LDG(P + 1);
+RTB_DEV bool sphere_test(const double2* __restrict__ P, const double2 c01, const double2 c2r, int moving, const Ray& r,
+                         double time, double tmin, double tmax, double& t_out) {
   double cx = c01.x, cy = c01.y, cz = c2r.x;
   if (moving) {  // Sphere::center  src/object.rs:107-112: self.center + time * dir
     const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
@@ -198,6 +203,10 @@ RTB_DEV bool sphere_test(const double2* __restrict__ P, int moving, const Ray& r
   t_out = root;
   return true;
 }
+RTB_DEV bool sphere_test(const double2* __restrict__ P, int moving, const Ray& r, double time, double tmin, double tmax,
+                         double& t_out) {
+  return sphere_test(P, RTB_LDG(P + 0), RTB_LDG(P + 1), moving, r, time, tmin, tmax, t_out);
+}
 
 // Tie rule equivalent to HittableList::hit's in-order scan (src/hittable.rs:92-106, Q7): a later
 // quad replaces an equal-t hit (closed interval), a later sphere does not (open interval).
@@ -210,23 +219,57 @@ struct Hit {
   double t;     // +inf: none
   double a, b;  // quad planar coordinates of the winner
   int prim;     // index into prims (BVH order); -1 none
-  int kind, id; // of the winner (tie rule)
 };
 
-RTB_DEV void hit_reset(Hit& h) { h.t = RTB_INF; h.a = 0.; h.b = 0.; h.prim = -1; h.kind = -1; h.id = -1; }
+RTB_DEV void hit_reset(Hit& h) { h.t = RTB_INF; h.a = 0.; h.b = 0.; h.prim = -1; }
+
+// a primitive test passed with t <= best.t: strictly closer wins; an exact tie is decided by the
+// reference's in-order scan (tie_wins) from the two primitives' kinds and canonical ids
+RTB_DEV void accept_hit(const DScene& S, int pi, int kind, double t, double a, double b, Hit& best) {
+  bool take = t < best.t;
+  if (!take) {
+    const int4 me = RTB_LDG(S.prim_info + pi), other = RTB_LDG(S.prim_info + best.prim);
+    take = tie_wins(kind, me.w, other.x & 0xFF, other.w);
+  }
+  if (take) { best.t = t; best.a = a; best.b = b; best.prim = pi; }
+}
 
 RTB_DEV void test_prim(const DScene& S, int pi, const Ray& r, double tmin, Hit& best) {
   RTB_ASSERT(pi >= 0 && pi < S.n_prims);
-  const int4 info = RTB_LDG(S.prim_info + pi);
   const double2* P = S.prims + (size_t)pi * PRIM_D2;
+  // the first 32 payload bytes are needed whatever the kind: issue them together with prim_info
+  // instead of behind the kind branch (one load latency less on the leaf path)
+  const int4 info = RTB_LDG(S.prim_info + pi);
+  const double2 p0 = RTB_LDG(P + 0), p1 = RTB_LDG(P + 1);
   const int kind = info.x & 0xFF;
   double t, a = 0., b = 0.;
   bool hit;
-  if (kind == PRIM_QUAD) hit = quad_test(P, r, tmin, best.t, t, a, b);
-  else hit = sphere_test(P, info.x & PRIM_FLAG_MOVING, r, r.time, tmin, best.t, t);
-  if (hit && (t < best.t || tie_wins(kind, info.w, best.kind, best.id))) {
-    best.t = t; best.a = a; best.b = b; best.prim = pi; best.kind = kind; best.id = info.w;
+  if (kind == PRIM_QUAD) hit = quad_test(P, p0, p1, r, tmin, best.t, t, a, b);
+  else hit = sphere_test(P, p0, p1, info.x & PRIM_FLAG_MOVING, r, r.time, tmin, best.t, t);
+  if (hit) accept_hit(S, pi, kind, t, a, b, best);
+}
+
+// the same test for the single primitive of a leaf whose reference carries the kind bits: no prim_info read
+RTB_DEV void test_prim_k(const DScene& S, int pi, int kind_bits, const Ray& r, double tmin, Hit& best) {
+  RTB_ASSERT(pi >= 0 && pi < S.n_prims);
+  const double2* P = S.prims + (size_t)pi * PRIM_D2;
+  const double2 p0 = RTB_LDG(P + 0), p1 = RTB_LDG(P + 1);
+  double t, a = 0., b = 0.;
+  bool hit;
+  if (kind_bits & LEAF_KIND_QUAD) hit = quad_test(P, p0, p1, r, tmin, best.t, t, a, b);
+  else hit = sphere_test(P, p0, p1, kind_bits & LEAF_KIND_MOVING, r, r.time, tmin, best.t, t);
+  if (hit) accept_hit(S, pi, (kind_bits & LEAF_KIND_QUAD) ? PRIM_QUAD : PRIM_SPHERE, t, a, b, best);
+}
+
+// all primitives of a leaf
+RTB_DEV int test_leaf(const DScene& S, int leaf_ref, const Ray& r, double tmin, Hit& best) {
+  const int first = leaf_first(leaf_ref), count = leaf_count(leaf_ref);
+  if (count == 1) {
+    test_prim_k(S, first, leaf_kind_bits(leaf_ref), r, tmin, best);
+  } else {
+    for (int i = 0; i < count; i++) test_prim(S, first + i, r, tmin, best);
   }
+  return count;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,12 +390,8 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
       if (h0) { node = ch0; continue; }
       if (h1) { node = ch1; continue; }
     } else {
-      const int leaf = ~node;
-      const int first = leaf >> 3, count = (leaf & 7) + 1;
-      for (int i = 0; i < count; i++) {
-        if (STATS) st->prim_tests++;
-        test_prim(S, first + i, r, tmin, best);
-      }
+      const int count = test_leaf(S, node, r, tmin, best);
+      if (STATS) st->prim_tests += (unsigned long long)count;
       tbest32 = __double2float_ru(best.t);
     }
     if (sp == 0) break;

@@ -90,6 +90,18 @@ __device__ __forceinline__ Ray to_ray(const PathRec& p) {
 
 constexpr uint32_t PADDING_PIXEL = 0xFFFFFFFFu;  // inert lane of a border tile
 
+// 256-bit global load (sm_100: LDG.E.ENL2.256): one instruction per 32-byte sector.  The L1 data pipe
+// charges a wavefront per load instruction and distinct sector, and the lanes of a traversing warp sit on
+// different nodes -- so a 64-byte node read as 2 x 256 bit costs half the wavefronts of 4 x 128 bit.
+struct alignas(32) F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg256(const float4* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+
 // A ray queue of `cap` slots is stored as FOUR PLANES of cap x 16 bytes (uint4 SoA: plane j holds word j
 // of every record), not as cap records of 64 bytes: the 32 consecutive slots a warp reads or writes are
 // then 512 contiguous bytes per plane (4 L1 wavefronts per instruction) instead of 32 sectors 64 bytes
@@ -203,15 +215,21 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
 // leaf or has run out of nodes; then the leaves are tested together.  fp32 conservative slabs in
 // fused form (t = plane * inv_d - o * inv_d), f64 reference-order primitive tests.
 // ------------------------------------------------------------------------------------------------
-constexpr int WF_EXTEND_BLOCK = 128;
+#ifndef WF_EXTEND_BLOCK_DIM
+#define WF_EXTEND_BLOCK_DIM 128
+#endif
+constexpr int WF_EXTEND_BLOCK = WF_EXTEND_BLOCK_DIM;
 #ifndef WF_EXTEND_MIN_BLOCKS
-#define WF_EXTEND_MIN_BLOCKS 7  // 72 regs, no spills; forcing 8 blocks (64 regs) spills and measured 4 % slower
+#define WF_EXTEND_MIN_BLOCKS (1024 / WF_EXTEND_BLOCK_DIM)  // 32 warps per SM = 64 registers, no spills (measured: 28 warps 28.7, 32 warps 27.3 ms per c4 row)
 #endif
 #ifndef WF_FETCH_THRESHOLD_N
 #define WF_FETCH_THRESHOLD_N 28
 #endif
 constexpr int WF_FETCH_THRESHOLD = WF_FETCH_THRESHOLD_N;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
+#ifndef WF_LD256
+#define WF_LD256 1
+#endif
 #ifndef WF_BREAK_LEFT
 #define WF_BREAK_LEFT 16  // measured on c4: 0 -> 35.1, 12 -> 33.9, 16 -> 33.4, 20 -> 33.5, 24 -> 33.8 ms extend per step
 #endif
@@ -287,8 +305,14 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
       if (STATS) st_nodes++;
       if (NODES == NODES_BVH4) {
         const float4* N = S.nodes4 + 8 * (size_t)node;
+#if WF_LD256
+        const F8 A = ldg256(N + 0), B = ldg256(N + 2), C = ldg256(N + 4), D = ldg256(N + 6);
+        const float4 lx = A.lo, hx = A.hi, ly = B.lo, hy = B.hi, lz = C.lo, hz = C.hi;
+        const int4 rf = make_int4(__float_as_int(D.lo.x), __float_as_int(D.lo.y), __float_as_int(D.lo.z), __float_as_int(D.lo.w));
+#else
         const float4 lx = __ldg(N + 0), hx = __ldg(N + 1), ly = __ldg(N + 2), hy = __ldg(N + 3), lz = __ldg(N + 4), hz = __ldg(N + 5);
         const int4 rf = __ldg(reinterpret_cast<const int4*>(N + 6));
+#endif
         float t0, t1, t2, t3;
         bool h0, h1, h2, h3;
         slab_box(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, sr, tmin32, tbest32, t0, h0);
@@ -323,7 +347,12 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
         ch0 = (int)q0.w; ch1 = (int)q1.w;
       } else {
         const float4* N = S.nodes + 4 * (size_t)node;
+#if WF_LD256
+        const F8 A = ldg256(N + 0), B = ldg256(N + 2);
+        const float4 n0 = A.lo, n1 = A.hi, n2 = B.lo, n3 = B.hi;
+#else
         const float4 n0 = __ldg(N + 0), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+#endif
         slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin32, tbest32, tn0, h0);
         slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin32, tbest32, tn1, h1);
         ch0 = __float_as_int(n3.x); ch1 = __float_as_int(n3.y);
@@ -341,7 +370,7 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
       }
       }
       if (node < 0 && leaf == 0) {  // first leaf: postpone it and continue with the next node
-        leaf = node;
+        leaf = node;  // (prefetching its primitive here was measured: slower -- the L1 data pipe is the scarce resource)
         WF_POP();
       }
       // every lane still in this loop holds a leaf already: stop speculating and test the leaves.
@@ -358,12 +387,8 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
     r.ox = rox; r.oy = roy; r.oz = roz;
     r.dx = (double)rdx; r.dy = (double)rdy; r.dz = (double)rdz; r.time = (double)rtime;
     while (leaf < 0) {
-      const int l = ~leaf;
-      const int first = l >> 3, count = (l & 7) + 1;
-      for (int i = 0; i < count; i++) {
-        if (STATS) st_prims++;
-        test_prim(S, first + i, r, 0.0001, best);
-      }
+      const int count = test_leaf(S, leaf, r, 0.0001, best);
+      if (STATS) st_prims += (unsigned long long)count;
       leaf = 0;
       if (node < 0) {
         leaf = node;
@@ -413,15 +438,14 @@ struct PoolWarp {
   double ox[WF_POOL], oy[WF_POOL], oz[WF_POOL], tbest[WF_POOL];
   float dx[WF_POOL], dy[WF_POOL], dz[WF_POOL], time[WF_POOL];
   float idx[WF_POOL], idy[WF_POOL], idz[WF_POOL], oxi[WF_POOL], oyi[WF_POOL], ozi[WF_POOL];
-  int best_prim[WF_POOL], best_kind[WF_POOL], best_id[WF_POOL];
+  int best_prim[WF_POOL];
   int node[WF_POOL], sp[WF_POOL], pos[WF_POOL], status[WF_POOL];
   int list[32];
 };
 
 __device__ __forceinline__ int leaf_status(const DScene& S, int node) {
   // kind of the (first) primitive of a leaf; mixed leaves are tested by test_prim anyway
-  const int first = (~node) >> 3;
-  return (__ldg(S.prim_info + first).x & 0xFF) == PRIM_QUAD ? ST_LEAF_Q : ST_LEAF_S;
+  return (leaf_kind_bits(node) & LEAF_KIND_QUAD) ? ST_LEAF_Q : ST_LEAF_S;
 }
 
 template <bool STATS>
@@ -471,7 +495,7 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
               W.idx[e] = ix; W.idy[e] = iy; W.idz[e] = iz;
               W.oxi[e] = (float)p.ox * ix; W.oyi[e] = (float)p.oy * iy; W.ozi[e] = (float)p.oz * iz;
               W.tbest[e] = RTB_INF;
-              W.best_prim[e] = -1; W.best_kind[e] = -1; W.best_id[e] = -1;
+              W.best_prim[e] = -1;
               W.node[e] = 0; W.sp[e] = 0; W.pos[e] = k;
               W.status[e] = ST_INNER;
             } else {  // nothing to traverse: record the miss
@@ -542,15 +566,11 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
         r.dx = (double)W.dx[e]; r.dy = (double)W.dy[e]; r.dz = (double)W.dz[e]; r.time = (double)W.time[e];
         Hit best;
         best.t = W.tbest[e]; best.a = 0.; best.b = 0.;
-        best.prim = W.best_prim[e]; best.kind = W.best_kind[e]; best.id = W.best_id[e];
-        const int l = ~node;
-        const int first = l >> 3, count = (l & 7) + 1;
-        for (int i = 0; i < count; i++) {
-          if (STATS) st_prims++;
-          test_prim(S, first + i, r, 0.0001, best);
-        }
+        best.prim = W.best_prim[e];
+        const int count = test_leaf(S, node, r, 0.0001, best);
+        if (STATS) st_prims += (unsigned long long)count;
         W.tbest[e] = best.t;
-        W.best_prim[e] = best.prim; W.best_kind[e] = best.kind; W.best_id[e] = best.id;
+        W.best_prim[e] = best.prim;
         node = sp > 0 ? stack[--sp] : TRAV_DONE;
       }
       // ---- write the entry back / retire it -------------------------------------------------------------------
@@ -588,7 +608,7 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
 #define WF_SHADE_BLOCK_DIM 128  // measured on c4: 128 -> 23.0, 256 -> 23.9, 512 -> 26.0 ms shade per step
 #endif
 #ifndef WF_SHADE_MIN_BLOCKS
-#define WF_SHADE_MIN_BLOCKS 6
+#define WF_SHADE_MIN_BLOCKS 7  // 72 registers (148 B of spills): measured 20.3 vs 21.1 ms per c4 row at 6 blocks / 80 registers
 #endif
 constexpr int WF_SHADE_BLOCK = WF_SHADE_BLOCK_DIM;
 constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;

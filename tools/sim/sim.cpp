@@ -238,13 +238,12 @@ int sim_extend(void* p, const QRay* rays, long long n, const Policy* pol_, SimOu
           if (L.n_leaf == 0 && L.node < 0) { L.leaf[L.n_leaf++] = L.node; pop(L); }  // node leaf moves into a slot
           if (L.n_leaf == 0) continue;
           lanes++;
-          const int l = ~L.leaf[0];
-          const int first = l >> 3, count = (l & 7) + 1;
+          const int first = leaf_first(L.leaf[0]), count = leaf_count(L.leaf[0]);
           for (int i = 0; i < count; i++) {
             o->prim_tests++;
             ((S.prim_info[first + i].x & 0xFF) == PRIM_QUAD ? nq : ns)++;
-            test_prim(S, first + i, L.r, 0.0001, L.best);
           }
+          test_leaf(S, L.leaf[0], L.r, 0.0001, L.best);
           for (int k = 1; k < L.n_leaf; k++) L.leaf[k - 1] = L.leaf[k];
           L.n_leaf--;
           L.tbest32 = __double2float_ru(L.best.t);
@@ -298,7 +297,8 @@ extern "C" int sim_check_q(void* p, const QRay* rays, long long n, long long bru
           if (h1) { node = ch1; continue; }
         } else {
           const int leaf = ~node;
-          for (int k = 0; k < (leaf & 7) + 1; k++) test_prim(S, (leaf >> 3) + k, r, 0.0001, hq);
+          (void)leaf;
+          test_leaf(S, node, r, 0.0001, hq);
           tbest32 = __double2float_ru(hq.t);
         }
         if (sp == 0) break;
@@ -460,8 +460,7 @@ extern "C" int sim_extend4(void* p, const QRay* rays, long long n, const Policy*
           if (L.leaf == 0 && L.node < 0) { L.leaf = L.node; pop(L); }
           if (L.leaf == 0) continue;
           lanes++;
-          const int l = ~L.leaf;
-          for (int i = 0; i < (l & 7) + 1; i++) { o->prim_tests++; test_prim(S, (l >> 3) + i, L.r, 0.0001, L.best); }
+          o->prim_tests += test_leaf(S, L.leaf, L.r, 0.0001, L.best);
           L.leaf = 0;
           L.tbest32 = __double2float_ru(L.best.t);
         }
@@ -511,7 +510,8 @@ extern "C" int sim_check4(void* p, const QRay* rays, long long n, long long brut
           }
         } else {
           const int leaf = ~node;
-          for (int k = 0; k < (leaf & 7) + 1; k++) test_prim(S, (leaf >> 3) + k, r, 0.0001, h4);
+          (void)leaf;
+          test_leaf(S, node, r, 0.0001, h4);
           tbest32 = __double2float_ru(h4.t);
         }
         if (sp == 0) break;
