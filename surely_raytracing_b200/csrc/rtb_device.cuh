@@ -29,6 +29,8 @@
 
 #if defined(__CUDACC__)
 #define RTB_DEV __device__ __forceinline__
+// (Turning the rarely-taken paths -- generic medium boundaries, Perlin turbulence, light sampling, sphere uv --
+// into real calls to shrink the 73 KB shade kernel was measured: 20.1 -> 26.7 ms per c4 row.  Everything inlines.)
 #define RTB_LDG(p) __ldg(p)
 #else
 #include <cmath>

@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
 #define WF_SHADE_MIN_BLOCKS 7  // 72 registers (148 B of spills): measured 20.3 vs 21.1 ms per c4 row at 6 blocks / 80 registers
 #endif
 constexpr int WF_SHADE_BLOCK = WF_SHADE_BLOCK_DIM;
-constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
+[[maybe_unused]] constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
 
 struct ShadeItem {  // what moves through shared memory to the lane that shades it (80 B)
   uint4 a, b, c, d;
@@ -619,7 +619,7 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
   int id;
   int info_x;  // prim_info[id].x of a surface hit (kind | flags | class | material)
 };
-constexpr int WF_SMEM_MATERIALS = 32, WF_SMEM_TEXTURES = 32, WF_SMEM_MEDIA = 4;
+[[maybe_unused]] constexpr int WF_SMEM_MATERIALS = 32, WF_SMEM_TEXTURES = 32, WF_SMEM_MEDIA = 4;
 #ifndef WF_SHADE_TABLES_SMEM
 #define WF_SHADE_TABLES_SMEM 0  // measured on c4: staging the tables costs 1.8 ms / step (generic loads + a barrier)
 #endif
@@ -787,7 +787,8 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
         } else if (STATS) {
           st.nonfinite++;
         }
-        atomicAdd(acc + 3, 1.0f);
+        // (the per-pixel sample count, accum.w, is added in bulk by k_wf_add_count: every pixel receives
+        //  exactly one path per stratum, so one atomic per path would only repeat what the host knows)
       }
     }
   }
@@ -814,6 +815,12 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+// accum.w += number of strata rendered, for every pixel (what one atomicAdd(+1) per finished path would sum to)
+__global__ void k_wf_add_count(float4* __restrict__ accum, int n_pixels, float n_strata) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pixels) accum[i].w += n_strata;
+}
+
 __global__ void k_wf_sum_segments(WFQueues Q0, WFQueues Q1, WFQueues Q2, WFQueues Q3, int n, DStats* stats) {
   const WFQueues* q[4] = {&Q0, &Q1, &Q2, &Q3};
   unsigned long long s = 0;
@@ -980,10 +987,7 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
       for (int k = 0; k < K; k++) {
         if (!sub[k].active) continue;
         if ((e = cudaStreamSynchronize(sub[k].st)) != cudaSuccess) return e;
-        static const bool tail_sizing = env_int("RTB_WF_TAIL", 1, 0, 1) != 0;
-        if (h_c[k].next_path >= h_c[k].total_paths && !tail_sizing) {
-          if (h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
-        } else if (h_c[k].next_path >= h_c[k].total_paths) {
+        if (h_c[k].next_path >= h_c[k].total_paths) {
           if (h_c[k].n_out == 0) { sub[k].active = false; n_active--; }
           bound[k] = std::max<long long>(h_c[k].n_out, 1);  // every path has started: the queue only shrinks
           if (!profile) poll_every = bound[k] < cap / 4 ? 2 : 4;
@@ -1000,6 +1004,11 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
       if ((e = cudaEventRecord(ctx.ev_done[k], sub[k].st)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(stream, ctx.ev_done[k], 0)) != cudaSuccess) return e;
     }
+  }
+  {
+    const int n_pixels = S.cam.width * S.cam.height;
+    k_wf_add_count<<<(n_pixels + 255) / 256, 256, 0, stream>>>(d_accum, n_pixels, (float)n_strata);
+    n_launch++;
   }
   if (collect_stats) {
     k_wf_sum_segments<<<1, 1, 0, stream>>>(sub[0].Q, sub[K > 1 ? 1 : 0].Q, sub[K > 2 ? 2 : 0].Q, sub[K > 3 ? 3 : 0].Q, K, d_stats);

@@ -39,6 +39,8 @@ def load():
         lib.emu_medium_interval.argtypes = [vp, C.c_int, vp, i64, vp, vp]
         lib.emu_eval_texture.argtypes = [vp, C.c_int, vp, i64, vp]
         lib.emu_eval_light_pdf.argtypes = [vp, vp, i64, vp]
+        lib.emu_check_qnodes.argtypes = [vp, vp, i64, i64, vp]
+        lib.emu_check_nodes4.argtypes = [vp, vp, i64, i64, vp]
         _lib = lib
     return _lib
 
@@ -82,6 +84,21 @@ class EmuScene:
         uvp = np.ascontiguousarray(uvp, dtype=np.float64).reshape(-1, 5)
         out = np.zeros((len(uvp), 3))
         self._lib.emu_eval_texture(self._h, texture, _ptr(uvp), len(uvp), _ptr(out))
+        return out
+
+    QRAY_DTYPE = np.dtype([("o", "<f8", 3), ("d", "<f4", 3), ("time", "<f4")])  # a ray as the wavefront queues store it
+
+    def check_trees(self, rays, brute_every=5):
+        """Closest hits through the 32-byte quantised nodes and through the collapsed BVH4 against the fp32
+        BVH2 and a brute-force scan.  Returns two dicts of counts."""
+        q = np.zeros(len(rays), dtype=self.QRAY_DTYPE)
+        q["o"] = rays["origin"]; q["d"] = rays["direction"]; q["time"] = rays["time"]
+        out = {}
+        for name, fn in (("qnodes", self._lib.emu_check_qnodes), ("nodes4", self._lib.emu_check_nodes4)):
+            r = np.zeros(6)
+            fn(self._h, _ptr(q), len(q), brute_every, _ptr(r))
+            out[name] = {"visits": r[0], "visits_bvh2": r[1], "mismatch_bvh2": int(r[2]), "mismatch_brute": int(r[3]),
+                         "n_brute": int(r[4]), "extra": int(r[5])}
         return out
 
     def eval_light_pdf(self, od):

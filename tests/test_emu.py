@@ -79,3 +79,29 @@ def test_remaining_main_rs_scenes(name):
     se, st = e.render()
     rel = np.abs(so - se).max(axis=2) / (np.abs(so).max(axis=2) + 1e-3)
     assert (rel > 2e-3).mean() < 0.02 and abs(so.mean() - se.mean()) < 3e-3 * so.mean(), ((rel > 2e-3).mean(), so.mean(), se.mean())
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5"])
+def test_alternative_trees_find_the_same_closest_hits(cfg):
+    """The opt-in forms of the tree the wavefront extend can traverse -- 16-bit quantised 32-byte nodes and the
+    collapsed BVH4 (csrc/flatten.cpp) -- are conservative: same closest hit (prim AND t, bit for bit) as the
+    fp32 BVH2 and as a brute-force scan, on camera rays, surface-leaving rays, axis-parallel directions
+    and origins far outside the scene (the quantised form falls back to an unculled walk there)."""
+    b = BuiltScene(cfg, width=96, spp=4)
+    e = EmuScene(b)
+    rays = e_rays = orc.OracleScene(b, use_bvh=False).camera_rays()
+    sec = util.secondary_rays(e.trace(rays), np.random.default_rng(11), n_max=8000)
+    sec["direction"] = sec["direction"].astype(np.float32)          # queue directions are fp32-valued
+    rng = np.random.default_rng(5)
+    adv = sec[rng.integers(0, len(sec), 4000)].copy()
+    adv["direction"][:1000, 0] = 0.0
+    adv["direction"][1000:2000, 1] = 0.0
+    adv["origin"][2000:3000] *= 40.0
+    adv["origin"][3000:] += rng.normal(0, 3000, (1000, 3))
+    cam = e_rays.copy()
+    cam["direction"] = cam["direction"].astype(np.float32)
+    allr = np.concatenate([cam, sec, adv])
+    res = e.check_trees(allr, brute_every=5)
+    for name in ("qnodes", "nodes4"):
+        assert res[name]["mismatch_bvh2"] == 0 and res[name]["mismatch_brute"] == 0, (name, res[name])
+    assert res["nodes4"]["visits"] < 0.75 * res["nodes4"]["visits_bvh2"]   # the collapse does halve the node steps

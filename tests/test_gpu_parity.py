@@ -157,6 +157,22 @@ def test_deterministic_and_additive_over_sample_ranges(pipeline):
     assert not np.array_equal(a, c) and abs(a.mean() - c.mean()) < 0.05 * a.mean()
 
 
+@pytest.mark.parametrize("env", ["RTB_BVH4", "RTB_QNODES"])
+@pytest.mark.parametrize("cfg", ["c4", "c2"])
+def test_opt_in_tree_forms_give_the_same_image(cfg, env, monkeypatch):
+    """The extend kernel's other node formats (collapsed BVH4, 16-bit quantised nodes; chosen when the scene
+    is created) only change the cull: same closest hits, hence the same image up to the order of the fp32
+    atomic adds, and strictly fewer / equally many node visits for the BVH4."""
+    b = BuiltScene(cfg, width=160, spp=16)
+    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    monkeypatch.setenv(env, "1")
+    alt, st_alt = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert np.allclose(alt, ref, rtol=1e-5, atol=1e-4)
+    assert st_alt["segments"] == st_ref["segments"] and st_alt["prim_tests"] <= 1.1 * st_ref["prim_tests"]
+    if env == "RTB_BVH4":
+        assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
+
+
 def test_flags_iso_pdf_zero_and_full_size_round_trip_property():
     """F3 flag reaches the device; at BASELINE size (c3 600x600) a size-independent property:
     with black-albedo smoke only (density up) the image can only get darker."""

@@ -163,10 +163,10 @@ def check_q(width=160, cap=32768):
         extra["o"][15000:] += rng.normal(0, 3000, (5000, 3))
         allr = np.ascontiguousarray(np.concatenate([rays, extra]))
         out = np.zeros(6)
-        lib.sim_check_q(h, allr.ctypes.data_as(C.c_void_p), C.c_longlong(len(allr)), C.c_longlong(7), out.ctypes.data_as(C.c_void_p))
+        lib.emu_check_qnodes(h, allr.ctypes.data_as(C.c_void_p), C.c_longlong(len(allr)), C.c_longlong(7), out.ctypes.data_as(C.c_void_p))
         print(f"{cfg}: rays {len(allr)}  node visits/ray q {out[0]:.3f} fp32 {out[1]:.3f}  mismatches vs fp32-tree {int(out[2])}  "
               f"vs brute force {int(out[3])} of {int(out[4])}  unculled rays {int(out[5])}")
-        lib.sim_check4(h, allr.ctypes.data_as(C.c_void_p), C.c_longlong(len(allr)), C.c_longlong(7), out.ctypes.data_as(C.c_void_p))
+        lib.emu_check_nodes4(h, allr.ctypes.data_as(C.c_void_p), C.c_longlong(len(allr)), C.c_longlong(7), out.ctypes.data_as(C.c_void_p))
         print(f"{cfg}: bvh4 visits/ray {out[0]:.3f} (bvh2 {out[1]:.3f})  mismatches vs bvh2 {int(out[2])}  vs brute force {int(out[3])} of {int(out[4])}  "
               f"max stack {int(out[5])}")
 

@@ -14,8 +14,6 @@
 
 namespace {
 
-struct QRay { double ox, oy, oz; float dx, dy, dz, time; };
-
 int shading_class_of(const DScene& S, const Event& ev) {
   if (!(ev.t < RTB_INF)) return CLS_MISS;
   if (ev.medium >= 0) return S.media[ev.medium].cls_fast & 0xF;
@@ -261,69 +259,6 @@ int sim_extend(void* p, const QRay* rays, long long n, const Policy* pol_, SimOu
 
 }  // extern "C"
 
-// conservativeness check of the 32-byte nodes: closest hit through qnodes vs the fp32 nodes vs brute force
-extern "C" int sim_check_q(void* p, const QRay* rays, long long n, long long brute_every, double* out6) {
-  const Emu* e = static_cast<Emu*>(p);
-  const DScene& S = e->dev;
-  const float tmin32 = __double2float_rd(0.0001);
-  double visits_q = 0, visits_f = 0, mism_f = 0, mism_b = 0, n_brute = 0, unculled = 0;
-  for (long long i = 0; i < n; i++) {
-    Ray r;
-    r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
-    r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
-    Hit hq;
-    hit_reset(hq);
-    {
-      const SlabRay sr = slab_ray_q(S, r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz);
-      if (sr.idx != sr.idx) unculled++;
-      float tbest32 = __double2float_ru(hq.t);
-      int stack[BVH_STACK], sp = 0, node = 0;
-      for (;;) {
-        if (node >= 0) {
-          visits_q++;
-          const uint4* N = S.qnodes + 2 * (size_t)node;
-          float tn0, tn1;
-          bool h0, h1;
-          slab_box_q(N[0].x, N[0].y, N[0].z, sr, tmin32, tbest32, tn0, h0);
-          slab_box_q(N[1].x, N[1].y, N[1].z, sr, tmin32, tbest32, tn1, h1);
-          int ch0 = (int)N[0].w, ch1 = (int)N[1].w;
-          if (h0 && h1) {
-            if (tn1 < tn0) std::swap(ch0, ch1);
-            stack[sp++] = ch1;
-            node = ch0;
-            continue;
-          }
-          if (h0) { node = ch0; continue; }
-          if (h1) { node = ch1; continue; }
-        } else {
-          const int leaf = ~node;
-          (void)leaf;
-          test_leaf(S, node, r, 0.0001, hq);
-          tbest32 = __double2float_ru(hq.t);
-        }
-        if (sp == 0) break;
-        node = stack[--sp];
-      }
-    }
-    Hit hf;
-    hit_reset(hf);
-    DStats st = {0, 0, 0, 0, 0, 0};
-    closest_surface<true>(S, r, 0.0001, hf, &st);
-    visits_f += (double)st.node_visits;
-    if (hf.prim != hq.prim || hf.t != hq.t) mism_f++;
-    if (brute_every > 0 && (i % brute_every) == 0) {
-      Hit hb;
-      hit_reset(hb);
-      closest_surface_brute(S, r, 0.0001, hb);
-      n_brute++;
-      if (hb.prim != hq.prim || hb.t != hq.t) mism_b++;
-    }
-  }
-  out6[0] = visits_q / n; out6[1] = visits_f / n; out6[2] = mism_f; out6[3] = mism_b; out6[4] = n_brute; out6[5] = unculled;
-  return 0;
-}
-
-
 // ---- BVH4 model: collapse every other level of the BVH2, replay the same lane logic --------------------------
 namespace {
 struct Node4 { float lo[4][3], hi[4][3]; int ref[4]; int n; };
@@ -474,64 +409,3 @@ extern "C" int sim_extend4(void* p, const QRay* rays, long long n, const Policy*
   return 0;
 }
 
-// the collapsed tree (DScene::nodes4) must find the same closest hits as the BVH2 and as brute force
-extern "C" int sim_check4(void* p, const QRay* rays, long long n, long long brute_every, double* out6) {
-  const Emu* e = static_cast<Emu*>(p);
-  const DScene& S = e->dev;
-  const float tmin32 = __double2float_rd(0.0001);
-  double visits4 = 0, visits2 = 0, mism2 = 0, mismb = 0, nb = 0, maxsp = 0;
-  for (long long i = 0; i < n; i++) {
-    Ray r;
-    r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
-    r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
-    Hit h4;
-    hit_reset(h4);
-    {
-      const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz);
-      float tbest32 = __double2float_ru(h4.t);
-      int stack[256], sp = 0, node = 0;
-      for (;;) {
-        if (node >= 0) {
-          visits4++;
-          const float4* N = S.nodes4 + 8 * (size_t)node;
-          const float* L[6] = {&N[0].x, &N[1].x, &N[2].x, &N[3].x, &N[4].x, &N[5].x};
-          int refs[4];
-          std::memcpy(refs, &N[6], 16);
-          float t[4];
-          bool h[4];
-          for (int c = 0; c < 4; c++) slab_box(L[0][c], L[1][c], L[2][c], L[3][c], L[4][c], L[5][c], sr, tmin32, tbest32, t[c], h[c]);
-          int m = -1;
-          for (int c = 0; c < 4; c++) if (h[c] && (m < 0 || t[c] < t[m])) m = c;
-          if (m >= 0) {
-            for (int c = 0; c < 4; c++) if (h[c] && c != m) stack[sp++] = refs[c];
-            if (sp > maxsp) maxsp = sp;
-            node = refs[m];
-            continue;
-          }
-        } else {
-          const int leaf = ~node;
-          (void)leaf;
-          test_leaf(S, node, r, 0.0001, h4);
-          tbest32 = __double2float_ru(h4.t);
-        }
-        if (sp == 0) break;
-        node = stack[--sp];
-      }
-    }
-    Hit h2;
-    hit_reset(h2);
-    DStats st = {0, 0, 0, 0, 0, 0};
-    closest_surface<true>(S, r, 0.0001, h2, &st);
-    visits2 += (double)st.node_visits;
-    if (h2.prim != h4.prim || h2.t != h4.t) mism2++;
-    if (brute_every > 0 && (i % brute_every) == 0) {
-      Hit hb;
-      hit_reset(hb);
-      closest_surface_brute(S, r, 0.0001, hb);
-      nb++;
-      if (hb.prim != h4.prim || hb.t != h4.t) mismb++;
-    }
-  }
-  out6[0] = visits4 / n; out6[1] = visits2 / n; out6[2] = mism2; out6[3] = mismb; out6[4] = nb; out6[5] = maxsp;
-  return 0;
-}
