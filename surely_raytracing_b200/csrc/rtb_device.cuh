@@ -291,7 +291,38 @@ struct SlabRay { float idx, idy, idz, oxi, oyi, ozi; };
 // form turns those axes into NaN = "unconstrained" and the ray visits most of the tree (measured:
 // single rays stretching an extend launch from 0.47 to 3.4 ms).  A tiny non-zero stand-in keeps the
 // reciprocal finite; the slab along that axis then culls correctly and conservatively.
-RTB_DEV float safe_rcp(float d) { return 1.0f / (fabsf(d) >= 1e-20f ? d : copysignf(1e-20f, d)); }
+RTB_DEV float fast_rcp(float x) {  // MUFU.RCP (<= 1 ulp, 1/0 = inf as IEEE) -- only ever used by conservative culls
+#if defined(__CUDACC__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// fp32 shading arithmetic (sampling maps, optics, pdf weights) is held to the oracle statistically, not bit by
+// bit: MUFU.SQRT / MUFU.RCP (<= 2 ulp) instead of the IEEE sequences with their slow-path branches.
+RTB_DEV float fast_sqrt(float x) {
+#if defined(__CUDACC__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+RTB_DEV float fast_div(float a, float b) {
+#if defined(__CUDACC__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+// The reciprocal only feeds the conservative cull (4e-6 relative slack): MUFU.RCP (<= 1 ulp) instead of the IEEE
+// division sequence, whose slow path showed up with 10 % of the extend kernel's stall samples.
+RTB_DEV float safe_rcp(float d) {
+  return fast_rcp(fabsf(d) >= 1e-20f ? d : copysignf(1e-20f, d));
+}
 
 RTB_DEV SlabRay slab_ray(double ox, double oy, double oz, float dx, float dy, float dz) {
   SlabRay s;
@@ -420,7 +451,7 @@ RTB_DEV double boundary_probe(const DScene& S, const DMedium& m, const Ray& r, d
 
 RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded box vs the whole line
   const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
-  const float idx = 1.0f / (float)r.dx, idy = 1.0f / (float)r.dy, idz = 1.0f / (float)r.dz;
+  const float idx = fast_rcp((float)r.dx), idy = fast_rcp((float)r.dy), idz = fast_rcp((float)r.dz);
   const float a0 = (m.lo[0] - ox) * idx, a1 = (m.hi[0] - ox) * idx;
   const float b0 = (m.lo[1] - oy) * idy, b1 = (m.hi[1] - oy) * idy;
   const float c0 = (m.lo[2] - oz) * idz, c1 = (m.hi[2] - oz) * idz;
@@ -463,7 +494,7 @@ RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, do
 RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, double tmin, double tmax, float U) {
   const float log_u = logf(U);  // U = 0 -> -inf -> hit_distance +inf: no event
   {  // the shortcut below, first in fp32 with a wide margin (most rays leave here)
-    const float len32 = sqrtf((float)r.dx * (float)r.dx + (float)r.dy * (float)r.dy + (float)r.dz * (float)r.dz);
+    const float len32 = fast_sqrt((float)r.dx * (float)r.dx + (float)r.dy * (float)r.dy + (float)r.dz * (float)r.dz);
     const float span32 = ((float)tmax - (float)tmin) * len32;
     const float hd32 = (float)m.neg_inv_density * log_u;
     if (hd32 > fminf(span32, m.diag) * 1.0001f + 1e-6f) return RTB_INF;
@@ -502,13 +533,13 @@ RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, d
 #else
     const float fast_log = logf(U);
 #endif
-    const float len32 = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float len32 = fast_sqrt(dx * dx + dy * dy + dz * dz);
     const float span32 = ((float)tmax - (float)tmin) * len32;
     const float nid = (float)m.neg_inv_density;
     // __logf: abs error <= 2^-21.4 on (0.5, 2), else 2 ulp -> slack nid * 1e-6 plus 0.1 % relative
     if (nid * fast_log > fminf(span32, m.diag) * 1.001f - nid * 1e-6f + 1e-5f) return RTB_INF;
     const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
-    const float idx = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
+    const float idx = fast_rcp(dx), idy = fast_rcp(dy), idz = fast_rcp(dz);
     const float a0 = (m.lo[0] - fx) * idx, a1 = (m.hi[0] - fx) * idx;
     const float b0 = (m.lo[1] - fy) * idy, b1 = (m.hi[1] - fy) * idy;
     const float c0 = (m.lo[2] - fz) * idz, c1 = (m.hi[2] - fz) * idz;
@@ -612,12 +643,12 @@ RTB_DEV V3 onb_local(const Onb& o, float a, float b, float c) { return a * o.u +
 RTB_DEV V3 random_cosine_direction(float r1, float r2) {  // vec3.rs:240-250
   float s, c;
   sincospif(2.f * r1, &s, &c);
-  const float sr = sqrtf(r2);
-  return v3(c * sr, s * sr, sqrtf(1.f - r2));
+  const float sr = fast_sqrt(r2);
+  return v3(c * sr, s * sr, fast_sqrt(1.f - r2));
 }
 RTB_DEV V3 random_unit_vector(float r1, float r2) {  // uniform sphere; vec3.rs:215-217 by direct map
   const float z = 1.f - 2.f * r1;
-  const float rr = sqrtf(fmaxf(0.f, 1.f - z * z));
+  const float rr = fast_sqrt(fmaxf(0.f, 1.f - z * z));
   float s, c;
   sincospif(2.f * r2, &s, &c);
   return v3(rr * c, rr * s, z);
@@ -682,7 +713,7 @@ RTB_DEV V3 lights_random(const DScene& S, double ox, double oy, double oz, float
     const float z = 1.f + r2 * ((float)sqrt(1. - L.prim[3] * L.prim[3] / dist2) - 1.f);
     float s, c;
     sincospif(2.f * r1, &s, &c);
-    const float sq = sqrtf(1.f - z * z);
+    const float sq = fast_sqrt(1.f - z * z);
     return onb_local(uvw, c * sq, s * sq, z);
   }
   return v3(1.f, 0.f, 0.f);  // Hittable default  src/hittable.rs:50-52
@@ -747,7 +778,7 @@ RTB_DEV void generate_primary(const DScene& S, uint32_t pixel, uint32_t sample, 
   double ox = cam.center[0], oy = cam.center[1], oz = cam.center[2];
   if (cam.defocus) {  // :226-230, 238-241; unit disk by the polar map instead of rejection
     const Rand4 d = rand4(S, pixel, sample, PRIMARY_BOUNCE, 1);
-    const float rr = sqrtf(d.x);
+    const float rr = fast_sqrt(d.x);
     float s, c;
     sincospif(2.f * d.y, &s, &c);
     const double dxk = (double)(rr * c), dyk = (double)(rr * s);
@@ -834,11 +865,15 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
         const double2 v01 = RTB_LDG(P + 2), v2 = RTB_LDG(P + 3);
         cx += r.time * v01.x; cy += r.time * v01.y; cz += r.time * v2.x;
       }
-      const double inv_r = 1. / c2r.y;
-      const double nx = (px - cx) * inv_r, ny = (py - cy) * inv_r, nz = (pz - cz) * inv_r;  // object.rs:169
-      front = (r.dx * nx + r.dy * ny + r.dz * nz) < 0.;
-      n = v3((float)nx, (float)ny, (float)nz);
-      if (needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105)
+      // outward normal (p - c) / r  (object.rs:169): the difference in f64 (p and c are large, their
+      // difference is not), the scaling in fp32 -- an f64 division per sphere hit buys nothing here
+      const double ex = px - cx, ey = py - cy, ez = pz - cz;
+      const float inv_r = fast_rcp((float)c2r.y);
+      n = v3((float)ex * inv_r, (float)ey * inv_r, (float)ez * inv_r);
+      front = (r.dx * ex + r.dy * ey + r.dz * ez) * c2r.y < 0.;  // sign of d.n with n = e / r (a negative radius flips it)
+      if (needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105); f64 like get_sphere_uv
+        const double inv_r64 = 1. / c2r.y;
+        const double nx = ex * inv_r64, ny = ey * inv_r64, nz = ez * inv_r64;
         const double2 cs = RTB_LDG(S.xforms + RTB_LDG(S.prim_info + ev.prim).z);
         double u64, v64;
         sphere_uv(cs.x * nx - cs.y * nz, ny, cs.y * nx + cs.x * nz, u64, v64);
@@ -863,13 +898,13 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
     dir = normalize(refl) + m.param * random_unit_vector(u.z, u.w);
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
   } else if (m.kind == MAT_DIELECTRIC) {  // material.rs:167-191 (Q15), vec3.rs:219-229
-    const float ratio = front ? 1.0f / m.param : m.param;
+    const float ratio = front ? fast_rcp(m.param) : m.param;
     const V3 ud = normalize(v3((float)r.dx, (float)r.dy, (float)r.dz));
     const float cos_theta = fminf(dot(-ud, n), 1.f);
-    const float sin_theta = sqrtf(1.f - cos_theta * cos_theta);
+    const float sin_theta = fast_sqrt(1.f - cos_theta * cos_theta);
     bool reflect_it = ratio * sin_theta > 1.f;
     if (!reflect_it) {
-      float r0 = (1.f - ratio) / (1.f + ratio);
+      float r0 = fast_div(1.f - ratio, 1.f + ratio);
       r0 = r0 * r0;
       const float x = 1.f - cos_theta, x2 = x * x;
       reflect_it = (r0 + (1.f - r0) * (x2 * x2 * x)) > u.x;
@@ -878,7 +913,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
       dir = ud - (2.f * dot(ud, n)) * n;
     } else {
       const V3 perp = ratio * (ud + cos_theta * n);
-      const V3 par = -sqrtf(fabsf(1.f - dot(perp, perp))) * n;
+      const V3 par = -fast_sqrt(fabsf(1.f - dot(perp, perp))) * n;
       dir = perp + par;
     }
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
@@ -915,7 +950,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
         return false;
       }
     }
-    const float wgt = scattering_pdf / pdf_val;
+    const float wgt = fast_div(scattering_pdf, pdf_val);
     ps.bx *= atten.x * wgt; ps.by *= atten.y * wgt; ps.bz *= atten.z * wgt;
     if (!(S.flags & 2u) && ps.bx == 0.f && ps.by == 0.f && ps.bz == 0.f) return false;  // dead path: result is 0
   }
