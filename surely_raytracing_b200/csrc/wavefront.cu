@@ -223,7 +223,7 @@ constexpr int WF_EXTEND_BLOCK = WF_EXTEND_BLOCK_DIM;
 #define WF_EXTEND_MIN_BLOCKS (1024 / WF_EXTEND_BLOCK_DIM)  // 32 warps per SM = 64 registers, no spills (measured: 28 warps 28.7, 32 warps 27.3 ms per c4 row)
 #endif
 #ifndef WF_FETCH_THRESHOLD_N
-#define WF_FETCH_THRESHOLD_N 28
+#define WF_FETCH_THRESHOLD_N 20  // measured on c4: 32 -> 26.9, 28 -> 26.8, 24 -> 26.7, 20 -> 26.5 ms extend per row
 #endif
 constexpr int WF_FETCH_THRESHOLD = WF_FETCH_THRESHOLD_N;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
