@@ -525,28 +525,32 @@ RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, dou
 // direction).  Two conservative fp32 rejections -- the free-flight shortcut (fast log, wide margin)
 // and the boundary-box line cull -- run before anything is widened to f64; both only ever skip
 // events that medium_event itself would reject, so the two pipelines take identical decisions.
+// medium_precheck: false = certainly no event in (tmin, tmax); true = evaluate medium_event.
+RTB_DEV bool medium_precheck(const DMedium& m, double ox, double oy, double oz, float dx, float dy, float dz, double tmin,
+                             double tmax, float U) {
+#if defined(__CUDACC__)
+  const float fast_log = __logf(U);
+#else
+  const float fast_log = logf(U);
+#endif
+  const float len32 = fast_sqrt(dx * dx + dy * dy + dz * dz);
+  const float span32 = ((float)tmax - (float)tmin) * len32;
+  const float nid = (float)m.neg_inv_density;
+  // __logf: abs error <= 2^-21.4 on (0.5, 2), else 2 ulp -> slack nid * 1e-6 plus 0.1 % relative
+  if (nid * fast_log > fminf(span32, m.diag) * 1.001f - nid * 1e-6f + 1e-5f) return false;
+  const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+  const float idx = fast_rcp(dx), idy = fast_rcp(dy), idz = fast_rcp(dz);
+  const float a0 = (m.lo[0] - fx) * idx, a1 = (m.hi[0] - fx) * idx;
+  const float b0 = (m.lo[1] - fy) * idy, b1 = (m.hi[1] - fy) * idy;
+  const float c0 = (m.lo[2] - fz) * idz, c1 = (m.hi[2] - fz) * idz;
+  const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
+  const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
+  return tn <= fmaf(fabsf(tf), 2e-6f, tf) + 1e-30f;
+}
+
 RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, double oy, double oz, float dx, float dy, float dz,
                                  double time, double tmin, double tmax, float U) {
-  {
-#if defined(__CUDACC__)
-    const float fast_log = __logf(U);
-#else
-    const float fast_log = logf(U);
-#endif
-    const float len32 = fast_sqrt(dx * dx + dy * dy + dz * dz);
-    const float span32 = ((float)tmax - (float)tmin) * len32;
-    const float nid = (float)m.neg_inv_density;
-    // __logf: abs error <= 2^-21.4 on (0.5, 2), else 2 ulp -> slack nid * 1e-6 plus 0.1 % relative
-    if (nid * fast_log > fminf(span32, m.diag) * 1.001f - nid * 1e-6f + 1e-5f) return RTB_INF;
-    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
-    const float idx = fast_rcp(dx), idy = fast_rcp(dy), idz = fast_rcp(dz);
-    const float a0 = (m.lo[0] - fx) * idx, a1 = (m.hi[0] - fx) * idx;
-    const float b0 = (m.lo[1] - fy) * idy, b1 = (m.hi[1] - fy) * idy;
-    const float c0 = (m.lo[2] - fz) * idz, c1 = (m.hi[2] - fz) * idz;
-    const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
-    const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
-    if (!(tn <= fmaf(fabsf(tf), 2e-6f, tf) + 1e-30f)) return RTB_INF;
-  }
+  if (!medium_precheck(m, ox, oy, oz, dx, dy, dz, tmin, tmax, U)) return RTB_INF;
   Ray r;
   r.ox = ox; r.oy = oy; r.oz = oz;
   r.dx = (double)dx; r.dy = (double)dy; r.dz = (double)dz;

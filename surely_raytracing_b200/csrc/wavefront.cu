@@ -611,7 +611,6 @@ __global__ void __launch_bounds__(WF_POOL_BLOCK) k_wf_extend_pool(const __grid_c
 #define WF_SHADE_MIN_BLOCKS 7  // 72 registers (148 B of spills): measured 20.3 vs 21.1 ms per c4 row at 6 blocks / 80 registers
 #endif
 constexpr int WF_SHADE_BLOCK = WF_SHADE_BLOCK_DIM;
-[[maybe_unused]] constexpr int WF_SHADE_WARPS = WF_SHADE_BLOCK / 32;
 
 struct ShadeItem {  // what moves through shared memory to the lane that shades it (80 B)
   uint4 a, b, c, d;
@@ -619,14 +618,6 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
   int id;
   int info_x;  // prim_info[id].x of a surface hit (kind | flags | class | material)
 };
-[[maybe_unused]] constexpr int WF_SMEM_MATERIALS = 32, WF_SMEM_TEXTURES = 32, WF_SMEM_MEDIA = 4;
-#ifndef WF_SHADE_TABLES_SMEM
-#define WF_SHADE_TABLES_SMEM 0  // measured on c4: staging the tables costs 1.8 ms / step (generic loads + a barrier)
-#endif
-#ifndef WF_SHADE_MATCH_SORT
-#define WF_SHADE_MATCH_SORT 1
-#endif
-
 template <bool STATS>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
@@ -634,39 +625,13 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
                                                             DStats* __restrict__ stats) {
   const unsigned FULL = 0xFFFFFFFFu;
   __shared__ ShadeItem items[WF_SHADE_BLOCK];
-#if WF_SHADE_MATCH_SORT
   __shared__ int class_count[NUM_CLASSES];
-#else
-  __shared__ int warp_count[NUM_CLASSES][WF_SHADE_WARPS];  // [cls][warp]
-  __shared__ int class_base[NUM_CLASSES];
-#endif
-#if WF_SHADE_TABLES_SMEM
-  __shared__ DMaterial s_materials[WF_SMEM_MATERIALS];
-  __shared__ DTexture s_textures[WF_SMEM_TEXTURES];
-  __shared__ DMedium s_media[WF_SMEM_MEDIA];
-#endif
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int i = blockIdx.x * WF_SHADE_BLOCK + tid;
   const int n = Q.c->n_in;
   if (blockIdx.x * WF_SHADE_BLOCK >= n) return;  // whole block idle (uniform)
-  // ---- 0. stage the small scene tables in shared memory (else: a chain of dependent global gathers per item)
-  Tables T = scene_tables(S);
-#if WF_SHADE_TABLES_SMEM
-  if (S.n_materials <= WF_SMEM_MATERIALS && S.n_textures <= WF_SMEM_TEXTURES && S.n_media <= WF_SMEM_MEDIA) {
-    const int wm = S.n_materials * (int)(sizeof(DMaterial) / 4), wt = S.n_textures * (int)(sizeof(DTexture) / 4),
-              wd = S.n_media * (int)(sizeof(DMedium) / 4);
-    const int* gm = reinterpret_cast<const int*>(S.materials);
-    const int* gt = reinterpret_cast<const int*>(S.textures);
-    const int* gd = reinterpret_cast<const int*>(S.media);
-    for (int k = tid; k < wm; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_materials)[k] = __ldg(gm + k);
-    for (int k = tid; k < wt; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_textures)[k] = __ldg(gt + k);
-    for (int k = tid; k < wd; k += WF_SHADE_BLOCK) reinterpret_cast<int*>(s_media)[k] = __ldg(gd + k);
-    T.materials = s_materials; T.textures = s_textures; T.media = s_media;
-  }
-#endif
-#if WF_SHADE_MATCH_SORT
+  const Tables T = scene_tables(S);
   if (tid < NUM_CLASSES) class_count[tid] = 0;
-#endif
   // ---- 1. load + medium events + class -----------------------------------------------------------
   ShadeItem it;
   int cls = -1;
@@ -676,39 +641,31 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     it.c = ld_stream(ray_plane(rays_in, cap, 2) + i); it.d = ld_stream(ray_plane(rays_in, cap, 3) + i);
     const uint4 h = ld_stream(reinterpret_cast<const uint4*>(Q.hits + i));
     it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
-#if defined(WF_SHADE_PREFETCH)
-    // the shading lane (same SM, after the sort) gathers this primitive: start the fetch now
-    if (it.id >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.prims + (size_t)it.id * PRIM_D2));
-#endif
   }
-#if WF_SHADE_TABLES_SMEM || WF_SHADE_MATCH_SORT
-  __syncthreads();  // tables staged, counters zeroed
-#endif
-  if (i < n) {
-    if (it.d.y == PADDING_PIXEL) {
-      cls = CLS_MISS;
-    } else {
-      if (S.n_media > 0) {
-        PathRec p;
-        unpack_geom(it.a, it.b, it.c, p);
-        unpack_state(it.d, p);
-        Rand4 u;
-        for (int mi = 0; mi < S.n_media; mi++) {
-          if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
-          const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-          const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
-          if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
-        }
-      }
-      cls = it.id == -1 ? CLS_MISS
-                        : (it.id >= 0 ? ((it.info_x >> PRIM_CLASS_SHIFT) & 0xF) : (T.media[-2 - it.id].cls_fast & 0xF));
+  __syncthreads();  // counters zeroed
+  const bool live = i < n && it.d.y != PADDING_PIXEL;
+  // Constant-medium events, each lane for its own ray (ConstantMedium::hit, constant_medium.rs:41-95).  The f64
+  // boundary intervals run at ~13 of 32 lanes (only the rays whose fp32 rejections do not settle it); queueing
+  // those (ray, medium) pairs in shared memory and evaluating the queue densely after a barrier was measured:
+  // 18.8 -> 23.1 ms per c4 row -- a 4-warp block idles through the whole f64 chain.  Kept per-lane.
+  if (live && S.n_media > 0) {
+    PathRec p;
+    unpack_geom(it.a, it.b, it.c, p);
+    unpack_state(it.d, p);
+    Rand4 u;
+    for (int mi = 0; mi < S.n_media; mi++) {
+      if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
+      const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
+      const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
+      if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
     }
   }
+  if (i < n)
+    cls = !live || it.id == -1 ? CLS_MISS
+                               : (it.id >= 0 ? ((it.info_x >> PRIM_CLASS_SHIFT) & 0xF) : (T.media[-2 - it.id].cls_fast & 0xF));
   // ---- 2. block-local counting sort by class: one shared-memory atomic per (warp, class present) ----------
-#if defined(WF_SHADE_NO_SORT)
-  if (cls >= 0) items[tid] = it;  // A/B arm: no class sort
-  __syncthreads();
-#elif WF_SHADE_MATCH_SORT
+  // (measured alternatives: per-class ballots + a prefix pass, 23.9 vs 25.1 ms per c4 row; no sort at all
+  //  25.2 ms and a less coherent next queue -- extend 34.6 vs 33.4 ms; scene tables staged in shared memory +1.8 ms)
   int dst = 0;
   {
     const unsigned peers = __match_any_sync(FULL, cls);
@@ -726,29 +683,6 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     items[dst] = it;
   }
   __syncthreads();
-#else
-  int rank_in_warp = 0;
-#pragma unroll
-  for (int k = 0; k < NUM_CLASSES; k++) {
-    const unsigned m = __ballot_sync(FULL, cls == k);
-    if (lane == 0) warp_count[k][warp] = __popc(m);
-    if (cls == k) rank_in_warp = __popc(m & ((1u << lane) - 1u));
-  }
-  __syncthreads();
-  if (tid < NUM_CLASSES) {  // exclusive prefix over classes (8 x 8 counters: one thread per class is enough)
-    int total_before = 0;
-    for (int k = 0; k < tid; k++)
-      for (int w = 0; w < WF_SHADE_WARPS; w++) total_before += warp_count[k][w];
-    class_base[tid] = total_before;
-  }
-  __syncthreads();
-  if (cls >= 0) {
-    int dst = class_base[cls] + rank_in_warp;
-    for (int w = 0; w < warp; w++) dst += warp_count[cls][w];
-    items[dst] = it;
-  }
-  __syncthreads();
-#endif
   const int n_block = min(WF_SHADE_BLOCK, n - blockIdx.x * WF_SHADE_BLOCK);
   // ---- 3. shade the item at sorted position `tid` -----------------------------------------------------
   bool alive = false;
