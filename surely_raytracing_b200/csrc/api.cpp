@@ -263,12 +263,10 @@ static int check_range(const rtb_scene* s, const RtbRenderParams* p) {
 // tail of a call (no new paths left to start) costs in proportion to it: measured on c4, 1/16 of the
 // call's paths is the sweet spot (64 M paths: 4 M slots; 512 M and more: 32 M slots = 4.6 GB of queues).
 static int64_t wavefront_capacity(int64_t total_paths) {
-  static const int64_t forced = [] {
-    const char* e = getenv("RTB_WF_CAPACITY");
-    const long long v = e ? atoll(e) : 0;
-    return (int64_t)(v >= 1024 ? v : 0);
-  }();
-  if (forced) return forced;
+  if (const char* e = getenv("RTB_WF_CAPACITY")) {  // read per call: tests shrink the queue to exercise refill and tail
+    const long long v = atoll(e);
+    if (v >= 1024) return (int64_t)v;
+  }
   int64_t cap = 1 << 20;
   while (cap < (1 << 25) && cap * 16 < total_paths) cap <<= 1;
   return cap;

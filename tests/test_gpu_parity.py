@@ -173,6 +173,23 @@ def test_opt_in_tree_forms_give_the_same_image(cfg, env, monkeypatch):
         assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
 
 
+@pytest.mark.parametrize("capacity", [1024, 5000, 65536])
+def test_small_queues_refill_and_drain_to_the_same_image(capacity, monkeypatch):
+    """The wavefront queue is topped up every iteration and its launches shrink with the draining tail; a queue
+    far smaller than the job (down to the 1024-slot minimum, and a size that is no multiple of a block)
+    exercises every refill / partial-block / tail-sizing path.  Philox keys make the image independent of
+    the schedule, up to the order of the fp32 atomic adds."""
+    b = BuiltScene("c3", width=96, spp=36, variant=1)
+    g = Scene(b)
+    ref, st_ref = g.render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    mega, _ = g.render(pipeline=capi.PIPELINE_MEGAKERNEL)
+    monkeypatch.setenv("RTB_WF_CAPACITY", str(capacity))
+    small, st = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert st["paths"] == st_ref["paths"] and st["segments"] == st_ref["segments"]
+    assert st["kernel_launches"] > st_ref["kernel_launches"]
+    assert np.allclose(small, ref, rtol=1e-5, atol=1e-4) and np.allclose(small, mega, rtol=1e-4, atol=1e-3)
+
+
 def test_flags_iso_pdf_zero_and_full_size_round_trip_property():
     """F3 flag reaches the device; at BASELINE size (c3 600x600) a size-independent property:
     with black-albedo smoke only (density up) the image can only get darker."""
