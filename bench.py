@@ -39,6 +39,9 @@ ROWS_PER_STEP = 10
 # librtb200.so (see DESIGN.md "Roofline"); frozen here so the bench JSON is self-describing.
 I_CONST = {"node_visit": 78.0, "prim_test": 150.0, "medium_probe": 45.0, "segment_shade": 260.0, "path_setup": 140.0}
 PEAK_LANE_INSTR_PER_CLK_PER_SM = 128
+# ncu-measured DRAM traffic of the wavefront pipeline on c4 (dram__bytes_read.sum + dram__bytes_write.sum over every
+# k_wf_* launch of profiles/r01b_wavefront_launches.csv.gz: 4140.4 GB over 7.004 steps of 2.8957 G segments each)
+MEASURED_DRAM_BYTES_PER_SEGMENT_C4 = 204.1
 
 
 def parse_args():
@@ -330,14 +333,19 @@ def run_b200(args, rank, world, local_rank):
         per_gpu_paths_s = paths_per_step_per_gpu / (sum(step_ms) / len(step_ms) * 1e-3)
         achieved = per_gpu_paths_s * i_path / 1e12
         seg_per_path = st["segments"] / paths
+        traffic = None
+        if args.workload == WORKLOAD and pipeline != capi.PIPELINE_MEGAKERNEL:   # bytes per step, like `achieved`
+            traffic = MEASURED_DRAM_BYTES_PER_SEGMENT_C4 * seg_per_path * paths_per_step_per_gpu
         roof = {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "Tlane-instr/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"{how}: {n_sm} SMs x 128 lanes x {sm_mhz:.0f} MHz",
+                "traffic": traffic, "traffic_source": "ncu dram bytes per segment (profiles/r01b_wavefront_launches.csv.gz) x segments per step",
+                "peak_source": f"{how}: {n_sm} SMs x 128 lanes x {sm_mhz:.0f} MHz",
                 "i_path_lane_instr": i_path, "segments_per_path": seg_per_path,
                 "node_visits_per_segment": st["node_visits"] / st["segments"],
                 "prim_tests_per_segment": st["prim_tests"] / st["segments"],
                 "medium_probes_per_segment": st["medium_probes"] / st["segments"],
                 "kernel": "k_render_mega" if pipeline == capi.PIPELINE_MEGAKERNEL else "k_wf_extend (+ k_wf_shade)",
                 "hbm_secondary": {"algorithmic_gbs": per_gpu_paths_s * seg_per_path * 176 / 1e9,
+                                  "measured_gbs": (traffic / (sum(step_ms) / len(step_ms) * 1e-3) / 1e9) if traffic else None,
                                   "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)), "bytes_per_segment": 176}}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args, args.cpu_seconds)
