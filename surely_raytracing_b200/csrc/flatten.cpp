@@ -513,6 +513,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   std::vector<int> node_remap;
   if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
   if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
+  if (B.surfaces.size() >= (size_t)1 << 26) { err = "more than 2^26 surface primitives (leaf references hold 26 index bits)"; return RTB_ERR_UNSUPPORTED; }
   lap("bvh build");
   out.bvh_depth = bvh.max_depth;
   for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
