@@ -40,6 +40,25 @@ def test_pass_rows_cover_the_grid_once_per_cycle():
         assert len(seen) == 100
 
 
+def test_pass_rows_in_blocks_of_rows():
+    """bench.py's default step is a block of 10 rows (one rtb_render call of 1000 strata): blocks tile the
+    stratum range [0, sqrt^2), never straddle it, and the ranks of one step never share a block."""
+    for world in (1, 2, 4, 8):
+        for rows in (1, 4, 10, 25, 100):
+            n_blocks = 100 // rows
+            per_step = []
+            for k in range(n_blocks * 2):
+                blocks = [pass_rows(k, world, r, 100, rows) for r in range(world)]
+                for lo, hi in blocks:
+                    assert hi - lo == rows * 100 and lo % (rows * 100) == 0 and 0 <= lo and hi <= 100 * 100
+                if world <= n_blocks:
+                    assert len({lo for lo, _ in blocks}) == world
+                per_step.append(blocks)
+            seen = {lo for blocks in per_step for lo, _ in blocks}
+            assert len(seen) == n_blocks            # a cycle visits every block
+    assert pass_rows(3, 1, 0, 31, 1000) == (0, 31 * 31)   # more rows than the grid has: the whole grid
+
+
 def _worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, str(ROOT))
