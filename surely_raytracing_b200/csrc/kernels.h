@@ -20,6 +20,8 @@ struct WavefrontContext {   // per-scene host state of the wavefront driver
   int extend_blocks_per_sm[2];
   int pool_blocks_per_sm[2];
   int extend_kind;          // 0 = per-lane rays (k_wf_extend), 1 = shared-memory ray pool (k_wf_extend_pool)
+  int shade_tma;            // 1 = persistent shade kernel with TMA-staged tiles (k_wf_shade_tma)
+  int shade_tma_blocks_per_sm;
   int n_sub;                // sub-pipelines (streams) the stratum range is split over
   cudaStream_t streams[WF_MAX_SUB];
   cudaEvent_t ev_done[WF_MAX_SUB];

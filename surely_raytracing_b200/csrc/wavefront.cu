@@ -618,12 +618,113 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
   int id;
   int info_x;  // prim_info[id].x of a surface hit (kind | flags | class | material)
 };
+// ---- the three per-item pieces shared by both shade kernels --------------------------------------------------
+// 1. constant-medium events (ConstantMedium::hit, constant_medium.rs:41-95), each lane for its own ray, then
+//    the shading class.  The f64 boundary intervals run at ~13 of 32 lanes (only the rays whose fp32
+//    rejections do not settle it); queueing those (ray, medium) pairs in shared memory and evaluating the
+//    queue densely after a barrier was measured: 18.8 -> 23.1 ms per c4 row (a 4-warp block idles through
+//    the whole f64 chain).  Kept per-lane.
+__device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
+                                          const uint4& d, double& t, int& id, int info_x) {
+  if (d.y == PADDING_PIXEL) return CLS_MISS;
+  if (S.n_media > 0) {
+    PathRec p;
+    unpack_geom(a, b, c, p);
+    unpack_state(d, p);
+    Rand4 u;
+    for (int mi = 0; mi < S.n_media; mi++) {
+      if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
+      const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
+      const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, t, U);
+      if (tm < t) { t = tm; id = -2 - mi; }
+    }
+  }
+  return id == -1 ? CLS_MISS : (id >= 0 ? ((info_x >> PRIM_CLASS_SHIFT) & 0xF) : (T.media[-2 - id].cls_fast & 0xF));
+}
+
+// 2. the block-local counting sort by class: position of this lane's item among the block's items, before the
+//    class prefix is added (one shared-memory atomic per warp and class present).
+//    (measured alternatives: per-class ballots + a prefix pass, 23.9 vs 25.1 ms per c4 row; no sort at all
+//     25.2 ms and a less coherent next queue -- extend 34.6 vs 33.4 ms; scene tables staged in shared memory +1.8 ms)
+__device__ __forceinline__ int wf_class_slot(int cls, int lane, int* class_count) {
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
+  int warp_base = 0;
+  const int leader = __ffs(peers) - 1;
+  if (cls >= 0 && lane == leader) warp_base = atomicAdd(&class_count[cls], __popc(peers));
+  warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, leader);
+  return warp_base + __popc(peers & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ int wf_class_prefix(int cls, const int* class_count) {
+  int base = 0;
+#pragma unroll
+  for (int k = 0; k < NUM_CLASSES - 1; k++)
+    if (k < cls) base += class_count[k];
+  return base;
+}
+
+// 3. ray_color's match arms for one item (render.rs:271-297): finished paths add their radiance to the image,
+//    survivors return true with the next ray packed into `out`.
+template <bool STATS>
+__device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
+                                              const uint4& d, double t, int id, int info_x, float4* __restrict__ accum,
+                                              RayRec& out, DStats& st) {
+  if (d.y == PADDING_PIXEL) return false;
+  PathRec p;
+  unpack_geom(a, b, c, p);
+  unpack_state(d, p);
+  PathState ps;
+  ps.ray = to_ray(p);
+  ps.bx = p.bx; ps.by = p.by; ps.bz = p.bz;
+  ps.pixel = p.pixel; ps.sample = p.sample; ps.bounce = p.bounce;
+  Event ev;
+  ev.t = t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
+  ev.prim = id >= 0 ? id : -1;
+  ev.medium = id <= -2 ? -2 - id : -1;
+  ev.info_x = id >= 0 ? info_x : 0;
+  float Lr = 0.f, Lg = 0.f, Lb = 0.f;
+  if (shade(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
+    p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
+    p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
+    p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
+    p.bounce = ps.bounce;
+    out = pack(p);
+    return true;
+  }
+  const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
+  float* acc = reinterpret_cast<float*>(accum + p.pixel);
+  if (finite || (S.flags & 2u)) {
+    if (Lr != 0.f) atomicAdd(acc + 0, Lr);
+    if (Lg != 0.f) atomicAdd(acc + 1, Lg);
+    if (Lb != 0.f) atomicAdd(acc + 2, Lb);
+  } else if (STATS) {
+    st.nonfinite++;
+  }
+  // (the per-pixel sample count, accum.w, is added in bulk by k_wf_add_count: every pixel receives
+  //  exactly one path per stratum, so one atomic per path would only repeat what the host knows)
+  return false;
+}
+
+// survivors: one atomic per warp, dense coalesced append.  (A per-block aggregate would need a barrier
+// after shading, and ncu showed every warp then waits for the block's slowest class.)
+__device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict__ rays_out, bool alive, const RayRec& out, int lane) {
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, alive);
+  if (!m) return;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&Q.c->n_out, __popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (alive) {
+    const int o = base + __popc(m & ((1u << lane) - 1u)), cap = Q.capacity;
+    st_stream(ray_plane(rays_out, cap, 0) + o, out.a); st_stream(ray_plane(rays_out, cap, 1) + o, out.b);
+    st_stream(ray_plane(rays_out, cap, 2) + o, out.c); st_stream(ray_plane(rays_out, cap, 3) + o, out.d);
+  }
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
                                                             DStats* __restrict__ stats) {
-  const unsigned FULL = 0xFFFFFFFFu;
   __shared__ ShadeItem items[WF_SHADE_BLOCK];
   __shared__ int class_count[NUM_CLASSES];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -632,6 +733,9 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
   if (blockIdx.x * WF_SHADE_BLOCK >= n) return;  // whole block idle (uniform)
   const Tables T = scene_tables(S);
   if (tid < NUM_CLASSES) class_count[tid] = 0;
+  // (Asking the L2 for the tile a block ~1000 positions further on will stream -- cp.async.bulk.prefetch.L2 of
+  //  its five planes by one thread -- was measured: 19.0 -> 19.3 ms per c4 row.  The DRAM latency of these
+  //  loads is not what this kernel waits for.)
   // ---- 1. load + medium events + class -----------------------------------------------------------
   ShadeItem it;
   int cls = -1;
@@ -643,45 +747,11 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
   }
   __syncthreads();  // counters zeroed
-  const bool live = i < n && it.d.y != PADDING_PIXEL;
-  // Constant-medium events, each lane for its own ray (ConstantMedium::hit, constant_medium.rs:41-95).  The f64
-  // boundary intervals run at ~13 of 32 lanes (only the rays whose fp32 rejections do not settle it); queueing
-  // those (ray, medium) pairs in shared memory and evaluating the queue densely after a barrier was measured:
-  // 18.8 -> 23.1 ms per c4 row -- a 4-warp block idles through the whole f64 chain.  Kept per-lane.
-  if (live && S.n_media > 0) {
-    PathRec p;
-    unpack_geom(it.a, it.b, it.c, p);
-    unpack_state(it.d, p);
-    Rand4 u;
-    for (int mi = 0; mi < S.n_media; mi++) {
-      if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
-      const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-      const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, it.t, U);
-      if (tm < it.t) { it.t = tm; it.id = -2 - mi; }
-    }
-  }
-  if (i < n)
-    cls = !live || it.id == -1 ? CLS_MISS
-                               : (it.id >= 0 ? ((it.info_x >> PRIM_CLASS_SHIFT) & 0xF) : (T.media[-2 - it.id].cls_fast & 0xF));
-  // ---- 2. block-local counting sort by class: one shared-memory atomic per (warp, class present) ----------
-  // (measured alternatives: per-class ballots + a prefix pass, 23.9 vs 25.1 ms per c4 row; no sort at all
-  //  25.2 ms and a less coherent next queue -- extend 34.6 vs 33.4 ms; scene tables staged in shared memory +1.8 ms)
-  int dst = 0;
-  {
-    const unsigned peers = __match_any_sync(FULL, cls);
-    int warp_base = 0;
-    const int leader = __ffs(peers) - 1;
-    if (cls >= 0 && lane == leader) warp_base = atomicAdd(&class_count[cls], __popc(peers));
-    warp_base = __shfl_sync(FULL, warp_base, leader);
-    dst = warp_base + __popc(peers & ((1u << lane) - 1u));
-  }
+  if (i < n) cls = wf_resolve(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
+  // ---- 2. block-local counting sort by class ---------------------------------------------------------
+  int dst = wf_class_slot(cls, lane, class_count);
   __syncthreads();
-  if (cls >= 0) {
-#pragma unroll
-    for (int k = 0; k < NUM_CLASSES - 1; k++)
-      if (k < cls) dst += class_count[k];
-    items[dst] = it;
-  }
+  if (cls >= 0) items[dst + wf_class_prefix(cls, class_count)] = it;
   __syncthreads();
   const int n_block = min(WF_SHADE_BLOCK, n - blockIdx.x * WF_SHADE_BLOCK);
   // ---- 3. shade the item at sorted position `tid` -----------------------------------------------------
@@ -690,59 +760,134 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
   DStats st = {0, 0, 0, 0, 0, 0};
   if (tid < n_block) {
     const ShadeItem me = items[tid];
-    if (me.d.y != PADDING_PIXEL) {
-      PathRec p;
-      unpack_geom(me.a, me.b, me.c, p);
-      unpack_state(me.d, p);
-      PathState ps;
-      ps.ray = to_ray(p);
-      ps.bx = p.bx; ps.by = p.by; ps.bz = p.bz;
-      ps.pixel = p.pixel; ps.sample = p.sample; ps.bounce = p.bounce;
-      Event ev;
-      ev.t = me.t; ev.a = 0.; ev.b = 0.; ev.have_ab = 0;
-      ev.prim = me.id >= 0 ? me.id : -1;
-      ev.medium = me.id <= -2 ? -2 - me.id : -1;
-      ev.info_x = me.id >= 0 ? me.info_x : 0;
-      float Lr = 0.f, Lg = 0.f, Lb = 0.f;
-      alive = shade(S, T, ps, ev, Lr, Lg, Lb, &st, STATS);
-      if (alive) {
-        p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
-        p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
-        p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
-        p.bounce = ps.bounce;
-        out = pack(p);
-      } else {
-        const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
-        float* acc = reinterpret_cast<float*>(accum + p.pixel);
-        if (finite || (S.flags & 2u)) {
-          if (Lr != 0.f) atomicAdd(acc + 0, Lr);
-          if (Lg != 0.f) atomicAdd(acc + 1, Lg);
-          if (Lb != 0.f) atomicAdd(acc + 2, Lb);
-        } else if (STATS) {
-          st.nonfinite++;
-        }
-        // (the per-pixel sample count, accum.w, is added in bulk by k_wf_add_count: every pixel receives
-        //  exactly one path per stratum, so one atomic per path would only repeat what the host knows)
-      }
-    }
+    alive = wf_shade_item<STATS>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
   }
-  // ---- survivors: one atomic per warp, dense coalesced append.  (A per-block aggregate would need a
-  //      barrier after shading, and ncu showed every warp then waits for the block's slowest class.)
-  const unsigned m = __ballot_sync(FULL, alive);
-  if (m) {
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&Q.c->n_out, __popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (alive) {
-      const int o = base + __popc(m & ((1u << lane) - 1u)), cap = Q.capacity;
-      st_stream(ray_plane(rays_out, cap, 0) + o, out.a); st_stream(ray_plane(rays_out, cap, 1) + o, out.b);
-      st_stream(ray_plane(rays_out, cap, 2) + o, out.c); st_stream(ray_plane(rays_out, cap, 3) + o, out.d);
-    }
-  }
+  wf_append(Q, rays_out, alive, out, lane);
   if (STATS) {
     if (st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
     if (tid == 0 && S.n_media > 0) atomicAdd(&stats->medium_probes, (unsigned long long)S.n_media * (unsigned long long)n_block);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade, persistent + TMA-staged variant.  Same three steps, but a block walks the queue in tiles of
+// WF_SHADE_BLOCK slots and the NEXT tile's five 2 KB planes (ray words a-d + hit records) are already in
+// flight -- cp.async.bulk into a second shared-memory stage, completion on an mbarrier -- while the
+// current tile is resolved, sorted and shaded, so the DRAM latency of the queue records is off the critical
+// path.  The sort permutes INDICES (order[]) and the shading lane reads its item straight from the stage,
+// so the 80-byte items are no longer copied through shared memory either.
+// MEASURED on c4 (60 GPU tests green with it): 23.6 ms per row against 19.0 ms for k_wf_shade at 7 blocks/SM.
+// The two 10 KB stages per block take 165 KB of the SM's 228 KB away from the L1, which this kernel's
+// primitive / material / texture gathers live on, and the latency it hides was not the one that
+// mattered (see the L2-prefetch note in k_wf_shade).  Opt-in: RTB_WF_SHADE_TMA=1.
+// ------------------------------------------------------------------------------------------------
+struct alignas(128) ShadeStage {
+  uint4 a[WF_SHADE_BLOCK], b[WF_SHADE_BLOCK], c[WF_SHADE_BLOCK], d[WF_SHADE_BLOCK], h[WF_SHADE_BLOCK];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+#ifndef WF_SHADE_TMA_MIN_BLOCKS
+#define WF_SHADE_TMA_MIN_BLOCKS 6
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_shade_tma(const __grid_constant__ DScene S, WFQueues Q,
+                                                                const RayRec* __restrict__ rays_in,
+                                                                RayRec* __restrict__ rays_out, float4* __restrict__ accum,
+                                                                DStats* __restrict__ stats) {
+  __shared__ ShadeStage stage[2];
+  __shared__ alignas(8) unsigned long long full[2];
+  __shared__ double res_t[WF_SHADE_BLOCK];
+  __shared__ int res_id[WF_SHADE_BLOCK];
+  __shared__ int order[WF_SHADE_BLOCK];
+  __shared__ int class_count[NUM_CLASSES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = Q.c->n_in;
+  const int n_tiles = (n + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK;
+  if ((int)blockIdx.x >= n_tiles) return;
+  const Tables T = scene_tables(S);
+  const int cap = Q.capacity;
+  // one thread arms the stage's mbarrier with the byte count and issues the five bulk copies of a tile
+  auto issue = [&](int tile, int s) {
+    const int base = tile * WF_SHADE_BLOCK;
+    const unsigned bytes = (unsigned)min(WF_SHADE_BLOCK, n - base) * 16u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done (barrier)
+    mbar_expect_tx(&full[s], 5u * bytes);
+    bulk_g2s(stage[s].a, ray_plane(rays_in, cap, 0) + base, bytes, &full[s]);
+    bulk_g2s(stage[s].b, ray_plane(rays_in, cap, 1) + base, bytes, &full[s]);
+    bulk_g2s(stage[s].c, ray_plane(rays_in, cap, 2) + base, bytes, &full[s]);
+    bulk_g2s(stage[s].d, ray_plane(rays_in, cap, 3) + base, bytes, &full[s]);
+    bulk_g2s(stage[s].h, Q.hits + base, bytes, &full[s]);
+  };
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < NUM_CLASSES) class_count[tid] = 0;
+  __syncthreads();
+  if (tid == 0) issue((int)blockIdx.x, 0);
+  DStats st = {0, 0, 0, 0, 0, 0};
+  unsigned long long probes = 0;
+  for (int tile = (int)blockIdx.x, k = 0; tile < n_tiles; tile += (int)gridDim.x, k++) {
+    const int s = k & 1;
+    const int next = tile + (int)gridDim.x;
+    if (tid == 0 && next < n_tiles) issue(next, s ^ 1);  // the other stage was released by the barrier that ended the last tile
+    mbar_wait(&full[s], (unsigned)(k >> 1) & 1u);
+    const int n_block = min(WF_SHADE_BLOCK, n - tile * WF_SHADE_BLOCK);
+    // ---- 1. medium events + class --------------------------------------------------------------------
+    int cls = -1;
+    if (tid < n_block) {
+      const uint4 h = stage[s].h[tid];
+      double t = __hiloint2double((int)h.y, (int)h.x);
+      int id = (int)h.z;
+      cls = wf_resolve(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
+      res_t[tid] = t;
+      res_id[tid] = id;
+    }
+    // ---- 2. counting sort of the tile's indices by class ------------------------------------------------
+    const int dst = wf_class_slot(cls, lane, class_count);
+    __syncthreads();
+    if (cls >= 0) order[dst + wf_class_prefix(cls, class_count)] = tid;
+    __syncthreads();
+    if (tid < NUM_CLASSES) class_count[tid] = 0;  // dead until the next tile's sort; ordered by the barrier below
+    // ---- 3. shade the item at sorted position `tid`, read straight from the stage ---------------------------
+    bool alive = false;
+    RayRec out;
+    if (tid < n_block) {
+      const int src = order[tid];
+      const uint4 h = stage[s].h[src];
+      alive = wf_shade_item<STATS>(S, T, stage[s].a[src], stage[s].b[src], stage[s].c[src], stage[s].d[src], res_t[src], res_id[src],
+                                   (int)h.w, accum, out, st);
+    }
+    wf_append(Q, rays_out, alive, out, lane);
+    if (STATS && tid == 0) probes += (unsigned long long)S.n_media * (unsigned long long)n_block;
+    __syncthreads();  // stage s, order[], res_*[] may be overwritten from here on
+  }
+  if (STATS) {
+    if (st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
+    if (tid == 0 && probes) atomicAdd(&stats->medium_probes, probes);
   }
 }
 
@@ -792,6 +937,15 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
   ctx->pool_blocks_per_sm[0] = ctx->pool_blocks_per_sm[1] = 4;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[0], k_wf_extend_pool<false>, WF_POOL_BLOCK, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[1], k_wf_extend_pool<true>, WF_POOL_BLOCK, 0);
+  ctx->shade_tma = env_int("RTB_WF_SHADE_TMA", 0, 0, 1);
+  ctx->shade_tma_blocks_per_sm = 4;
+  {
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wf_shade_tma<false>, WF_SHADE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_wf_shade_tma<true>, WF_SHADE_BLOCK, 0);
+    if (a > 0 && b > 0) ctx->shade_tma_blocks_per_sm = std::min(a, b);
+    ctx->shade_tma_blocks_per_sm = env_int("RTB_WF_SHADE_TMA_BLOCKS", ctx->shade_tma_blocks_per_sm, 1, 32);
+  }
   ctx->extend_kind = env_int("RTB_WF_EXTEND_POOL", 0, 0, 1);  // measured slower on c4: profiles/r01_pool_extend.txt
   // Sub-pipelines: independent slices of the stratum range on their own streams (RTB_WF_STREAMS).
   // Measured on c4 (profiles/r01_streams_sweep.txt): 2-4 streams are 1-9 % SLOWER than one -- the
@@ -902,8 +1056,14 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         }
       }
       if (profile) cudaEventRecord(pe[2], u.st);
-      if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-      else k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+      if (ctx.shade_tma) {  // persistent blocks, tiles strided over the grid
+        const unsigned grid = (unsigned)std::min<long long>(shade_blocks, (long long)ctx.sms * ctx.shade_tma_blocks_per_sm);
+        if (collect_stats) k_wf_shade_tma<true><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+        else k_wf_shade_tma<false><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+      } else {
+        if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+        else k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+      }
       if (profile) {
         cudaEventRecord(pe[3], u.st);
         cudaEventSynchronize(pe[3]);

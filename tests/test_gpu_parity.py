@@ -173,6 +173,21 @@ def test_opt_in_tree_forms_give_the_same_image(cfg, env, monkeypatch):
         assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
 
 
+def test_tma_staged_shade_kernel_gives_the_same_image(monkeypatch):
+    """The opt-in persistent shade kernel (cp.async.bulk tiles on an mbarrier, index sort) is the same
+    computation as the default one: same paths, same segments, same image up to fp32 atomic order --
+    also across partial last tiles and many tiles per block (small queue)."""
+    b = BuiltScene("c4", width=160, spp=16, variant=1)
+    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    monkeypatch.setenv("RTB_WF_SHADE_TMA", "1")
+    for cap in (None, 5000):
+        if cap:
+            monkeypatch.setenv("RTB_WF_CAPACITY", str(cap))
+        alt, st = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+        assert st["segments"] == st_ref["segments"] and st["medium_probes"] == st_ref["medium_probes"]
+        assert np.allclose(alt, ref, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("capacity", [1024, 5000, 65536])
 def test_small_queues_refill_and_drain_to_the_same_image(capacity, monkeypatch):
     """The wavefront queue is topped up every iteration and its launches shrink with the draining tail; a queue
