@@ -90,7 +90,7 @@ struct DTexture {
 struct DMedium {
   int first_prim, n_prims;  // boundary primitives (in `prims`, after the surfaces), DFS order
   int material;
-  int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere
+  int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere; bit 9: quads only
   double neg_inv_density;
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
   float diag;               // diagonal of that box: no chord of the boundary is longer
@@ -137,7 +137,7 @@ struct DScene {
   float grid_cell[3];
   int use_qnodes;  // wavefront extend traverses qnodes (else nodes)
   int use_bvh4;    // wavefront extend traverses nodes4
-  int pad2;
+  int has_box_media;  // some medium's boundary is quads only (cls_fast bit 9): shade uses its single-scan instantiation
   DCamera cam;
 };
 

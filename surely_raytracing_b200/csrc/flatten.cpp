@@ -683,6 +683,11 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     for (const Baked& b : B.boundaries[mi]) { emit_prim(d, out, b); bx.grow(b.lo, b.hi); }
     m.cls_fast = shading_class(d, m.material);
     if (m.n_prims == 1 && B.boundaries[mi][0].kind == PRIM_SPHERE && !(B.boundaries[mi][0].flags & PRIM_FLAG_MOVING)) m.cls_fast |= 0x100;
+    {
+      bool all_quads = m.n_prims > 0;
+      for (const Baked& b : B.boundaries[mi]) all_quads = all_quads && b.kind == PRIM_QUAD;
+      if (all_quads && !getenv("RTB_NO_BOX_SCAN")) m.cls_fast |= 0x200;
+    }
     for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
     {
       const double ex = (double)m.hi[0] - m.lo[0], ey = (double)m.hi[1] - m.lo[1], ez = (double)m.hi[2] - m.lo[2];

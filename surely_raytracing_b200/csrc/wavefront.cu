@@ -624,6 +624,7 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
 //    rejections do not settle it); queueing those (ray, medium) pairs in shared memory and evaluating the
 //    queue densely after a barrier was measured: 18.8 -> 23.1 ms per c4 row (a 4-warp block idles through
 //    the whole f64 chain).  Kept per-lane.
+template <bool BOXSCAN>
 __device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
                                           const uint4& d, double& t, int& id, int info_x) {
   if (d.y == PADDING_PIXEL) return CLS_MISS;
@@ -635,7 +636,7 @@ __device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, cons
     for (int mi = 0; mi < S.n_media; mi++) {
       if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
       const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-      const double tm = medium_event_lazy(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, t, U);
+      const double tm = medium_event_lazy<BOXSCAN>(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, t, U);
       if (tm < t) { t = tm; id = -2 - mi; }
     }
   }
@@ -720,7 +721,8 @@ __device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict_
   }
 }
 
-template <bool STATS>
+// BOXSCAN: the scene has a medium bounded by quads only (rtb_device.cuh, medium_interval)
+template <bool STATS, bool BOXSCAN>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
   }
   __syncthreads();  // counters zeroed
-  if (i < n) cls = wf_resolve(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
+  if (i < n) cls = wf_resolve<BOXSCAN>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
   // ---- 2. block-local counting sort by class ---------------------------------------------------------
   int dst = wf_class_slot(cls, lane, class_count);
   __syncthreads();
@@ -864,7 +866,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
       const uint4 h = stage[s].h[tid];
       double t = __hiloint2double((int)h.y, (int)h.x);
       int id = (int)h.z;
-      cls = wf_resolve(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
+      cls = wf_resolve<true>(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
       res_t[tid] = t;
       res_id[tid] = id;
     }
@@ -1063,8 +1065,13 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         if (collect_stats) k_wf_shade_tma<true><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
         else k_wf_shade_tma<false><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
       } else {
-        if (collect_stats) k_wf_shade<true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-        else k_wf_shade<false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+        if (S.has_box_media) {
+          if (collect_stats) k_wf_shade<true, true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+          else k_wf_shade<false, true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+        } else {
+          if (collect_stats) k_wf_shade<true, false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+          else k_wf_shade<false, false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
+        }
       }
       if (profile) {
         cudaEventRecord(pe[3], u.st);

@@ -44,7 +44,7 @@ def test_keyed_samples_match_path_by_path(cfg, variant):
     assert st["nonfinite_samples"] == 0
 
 
-def test_medium_intervals_and_textures_and_light_pdf():
+def test_medium_intervals_and_textures_and_light_pdf(monkeypatch):
     b = BuiltScene("c4", width=64, spp=4, variant=1)
     o, e = orc.OracleScene(b), EmuScene(b)
     rays = o.camera_rays()
@@ -54,6 +54,42 @@ def test_medium_intervals_and_textures_and_light_pdf():
         assert np.array_equal(np.isnan(a0), np.isnan(b0))
         ok = ~np.isnan(a0)
         assert np.allclose(a0[ok], b0[ok], rtol=1e-10) and np.allclose(a1[ok], b1[ok], rtol=1e-10)
+    # box-bounded media (c3): one scan of the six quads serves both boundary probes (rtb_device.cuh, medium_interval);
+    # camera rays, rays started inside / near the boxes in random directions, and rays aimed at box edges and
+    # corners (two or three faces hit within 1e-4: the second probe must then run as written)
+    b3 = BuiltScene("c3", width=64, spp=4)
+    o3, e3 = orc.OracleScene(b3), EmuScene(b3)
+    cam = o3.camera_rays()
+    rng3 = np.random.default_rng(21)
+    inside = cam[:4000].copy()
+    inside["origin"] = rng3.uniform([100., -20., 40.], [460., 350., 480.], (4000, 3))
+    inside["direction"] = rng3.normal(size=(4000, 3))
+    th = np.radians(15.0)   # box 1 of cornell_smoke: 165 x 330 x 165, rotate_y(15 deg), translate (265, 0, 295)
+    corners = np.array([[x * np.cos(th) + z * np.sin(th) + 265., y, -x * np.sin(th) + z * np.cos(th) + 295.]
+                        for x in (0., 165.) for y in (0., 330.) for z in (0., 165.)])
+    edge_pts = np.concatenate([corners, 0.5 * (corners[:, None] + corners[None, :]).reshape(-1, 3)])
+    aimed = cam[:len(edge_pts)].copy()
+    aimed["direction"] = edge_pts - aimed["origin"]
+    for rays3 in (cam, inside):
+        for m in range(2):
+            a0, a1 = o3.medium_interval(m, rays3)
+            b0, b1 = e3.medium_interval(m, rays3)
+            assert np.array_equal(np.isnan(a0), np.isnan(b0))
+            ok = ~np.isnan(a0)
+            assert np.allclose(a0[ok], b0[ok], rtol=1e-10, atol=1e-12) and np.allclose(a1[ok], b1[ok], rtol=1e-10, atol=1e-12)
+    # the single scan against the two probes as written (RTB_NO_BOX_SCAN=1 at scene creation): bit for bit, on
+    # every ray set -- exact edges included, where the oracle itself may differ in the last bit because the
+    # reference tests the box in its own rotated frame and the device in world space (instances)
+    monkeypatch.setenv("RTB_NO_BOX_SCAN", "1")
+    e3g = EmuScene(b3)
+    monkeypatch.delenv("RTB_NO_BOX_SCAN")
+    for rays3 in (cam, inside, aimed):
+        for m in range(2):
+            b0, b1 = e3.medium_interval(m, rays3)
+            g0, g1 = e3g.medium_interval(m, rays3)
+            assert np.array_equal(b0, g0, equal_nan=True) and np.array_equal(b1, g1, equal_nan=True)
+    assert (~np.isnan(e3.medium_interval(0, aimed)[0])).sum() >= 10
+    assert (~np.isnan(o3.medium_interval(0, inside)[0])).sum() > 500
     rng = np.random.default_rng(3)
     n_tex = b.desc.contents.n_textures
     uvp = np.hstack([rng.uniform(-0.2, 1.2, (4000, 2)), rng.uniform(-300, 600, (4000, 3))])
