@@ -624,11 +624,11 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
 //    rejections do not settle it); queueing those (ray, medium) pairs in shared memory and evaluating the
 //    queue densely after a barrier was measured: 18.8 -> 23.1 ms per c4 row (a 4-warp block idles through
 //    the whole f64 chain).  Kept per-lane.
-template <bool BOXSCAN>
+template <bool MEDIA, bool BOXSCAN>
 __device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
                                           const uint4& d, double& t, int& id, int info_x) {
   if (d.y == PADDING_PIXEL) return CLS_MISS;
-  if (S.n_media > 0) {
+  if (MEDIA && S.n_media > 0) {
     PathRec p;
     unpack_geom(a, b, c, p);
     unpack_state(d, p);
@@ -665,7 +665,7 @@ __device__ __forceinline__ int wf_class_prefix(int cls, const int* class_count) 
 
 // 3. ray_color's match arms for one item (render.rs:271-297): finished paths add their radiance to the image,
 //    survivors return true with the next ray packed into `out`.
-template <bool STATS>
+template <bool STATS, bool LIGHTS>
 __device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
                                               const uint4& d, double t, int id, int info_x, float4* __restrict__ accum,
                                               RayRec& out, DStats& st) {
@@ -683,7 +683,7 @@ __device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, 
   ev.medium = id <= -2 ? -2 - id : -1;
   ev.info_x = id >= 0 ? info_x : 0;
   float Lr = 0.f, Lg = 0.f, Lb = 0.f;
-  if (shade(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
+  if (shade<LIGHTS>(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
     p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
     p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
     p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
@@ -721,8 +721,11 @@ __device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict_
   }
 }
 
-// BOXSCAN: the scene has a medium bounded by quads only (rtb_device.cuh, medium_interval)
-template <bool STATS, bool BOXSCAN>
+// Scene-specialised instantiations (chosen at launch): SPEC bit 0 = the scene has constant media, bit 1 = one of
+// them is bounded by quads only (rtb_device.cuh, medium_interval), bit 2 = the light list is not empty.  Code a
+// scene never runs still costs it registers and instruction-cache misses in this 70 KB kernel.
+enum : int { SPEC_MEDIA = 1, SPEC_BOXSCAN = 2, SPEC_LIGHTS = 4, SPEC_ALL = 7 };
+template <bool STATS, int SPEC>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
   }
   __syncthreads();  // counters zeroed
-  if (i < n) cls = wf_resolve<BOXSCAN>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
+  if (i < n) cls = wf_resolve<(SPEC & SPEC_MEDIA) != 0, (SPEC & SPEC_BOXSCAN) != 0>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
   // ---- 2. block-local counting sort by class ---------------------------------------------------------
   int dst = wf_class_slot(cls, lane, class_count);
   __syncthreads();
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
   DStats st = {0, 0, 0, 0, 0, 0};
   if (tid < n_block) {
     const ShadeItem me = items[tid];
-    alive = wf_shade_item<STATS>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
+    alive = wf_shade_item<STATS, (SPEC & SPEC_LIGHTS) != 0>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
   }
   wf_append(Q, rays_out, alive, out, lane);
   if (STATS) {
@@ -866,7 +869,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
       const uint4 h = stage[s].h[tid];
       double t = __hiloint2double((int)h.y, (int)h.x);
       int id = (int)h.z;
-      cls = wf_resolve<true>(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
+      cls = wf_resolve<true, true>(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
       res_t[tid] = t;
       res_id[tid] = id;
     }
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
     if (tid < n_block) {
       const int src = order[tid];
       const uint4 h = stage[s].h[src];
-      alive = wf_shade_item<STATS>(S, T, stage[s].a[src], stage[s].b[src], stage[s].c[src], stage[s].d[src], res_t[src], res_id[src],
+      alive = wf_shade_item<STATS, true>(S, T, stage[s].a[src], stage[s].b[src], stage[s].c[src], stage[s].d[src], res_t[src], res_id[src],
                                    (int)h.w, accum, out, st);
     }
     wf_append(Q, rays_out, alive, out, lane);
@@ -898,6 +901,28 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+template <int SPEC>
+static void launch_shade_spec(const DScene& S, const WFQueues& Q, const RayRec* in, RayRec* out, float4* d_accum, DStats* d_stats,
+                              unsigned blocks, cudaStream_t st) {
+  k_wf_shade<false, SPEC><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
+}
+static void launch_shade(const DScene& S, const WFQueues& Q, const RayRec* in, RayRec* out, float4* d_accum, DStats* d_stats,
+                         bool collect_stats, unsigned blocks, cudaStream_t st) {
+  if (collect_stats) {  // the counted passes are not timed: one generic instantiation
+    k_wf_shade<true, SPEC_ALL><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
+    return;
+  }
+  const int spec = (S.n_media > 0 ? SPEC_MEDIA : 0) | (S.has_box_media ? SPEC_BOXSCAN : 0) | (S.n_lights > 0 ? SPEC_LIGHTS : 0);
+  switch (spec) {
+    case 0: launch_shade_spec<0>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+    case SPEC_MEDIA: launch_shade_spec<SPEC_MEDIA>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+    case SPEC_MEDIA | SPEC_BOXSCAN: launch_shade_spec<SPEC_MEDIA | SPEC_BOXSCAN>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+    case SPEC_LIGHTS: launch_shade_spec<SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+    case SPEC_LIGHTS | SPEC_MEDIA: launch_shade_spec<SPEC_LIGHTS | SPEC_MEDIA>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+    default: launch_shade_spec<SPEC_ALL>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
+  }
+}
+
 // accum.w += number of strata rendered, for every pixel (what one atomicAdd(+1) per finished path would sum to)
 __global__ void k_wf_add_count(float4* __restrict__ accum, int n_pixels, float n_strata) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1065,13 +1090,7 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         if (collect_stats) k_wf_shade_tma<true><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
         else k_wf_shade_tma<false><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
       } else {
-        if (S.has_box_media) {
-          if (collect_stats) k_wf_shade<true, true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-          else k_wf_shade<false, true><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-        } else {
-          if (collect_stats) k_wf_shade<true, false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-          else k_wf_shade<false, false><<<shade_blocks, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
-        }
+        launch_shade(S, u.Q, u.in, u.out, d_accum, d_stats, collect_stats, shade_blocks, u.st);
       }
       if (profile) {
         cudaEventRecord(pe[3], u.st);
