@@ -211,8 +211,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   for (int a = 0; a < 3; a++) { D.grid_base[a] = h.grid_base[a]; D.grid_inv_cell[a] = h.grid_inv_cell[a]; D.grid_cell[a] = h.grid_cell[a]; }
   D.use_qnodes = h.use_qnodes;
   D.use_bvh4 = h.use_bvh4;
-  D.has_box_media = 0;
-  for (const DMedium& m : h.media) D.has_box_media |= (m.cls_fast & 0x200) ? 1 : 0;
+  D.spec_bits = h.spec_bits;
   D.n_materials = (int)h.materials.size();
   D.n_textures = (int)h.textures.size();
   D.bvh_depth = h.bvh_depth;

@@ -47,6 +47,16 @@ enum : int { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_
 enum : int { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_IMAGE = 2, TEX_NOISE = 3 };
 enum : int { LIGHT_QUAD = 0, LIGHT_SPHERE = 1, LIGHT_OTHER = 2 };
 
+// Features a scene may or may not use; code for an unused one is compiled out of the shade instantiation the
+// scene runs (a set bit never changes a result, it only keeps code in).
+enum : int { SPEC_MEDIA = 1,        // constant media present
+             SPEC_BOXSCAN = 2,      // a medium bounded by quads only (single-scan boundary interval)
+             SPEC_LIGHTS = 4,       // non-empty light list (HittablePDF sampling)
+             SPEC_GENERIC_MEDIA = 8,  // a medium whose boundary is not one static sphere (generic boundary probes)
+             SPEC_QUAD_UV = 16,     // a quad whose material reads (u, v)
+             SPEC_SPHERE_UV = 32,   // a sphere whose material reads (u, v)
+             SPEC_ALL = 63 };
+
 constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
 constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf
 // Leaf reference (negative child index): ~(first << 5 | moving << 4 | quad << 3 | count - 1).  The two kind
@@ -137,7 +147,7 @@ struct DScene {
   float grid_cell[3];
   int use_qnodes;  // wavefront extend traverses qnodes (else nodes)
   int use_bvh4;    // wavefront extend traverses nodes4
-  int has_box_media;  // some medium's boundary is quads only (cls_fast bit 9): shade uses its single-scan instantiation
+  int spec_bits;   // SPEC_* features the scene uses: the wavefront shade kernel picks the smallest instantiation covering them
   DCamera cam;
 };
 

@@ -695,6 +695,19 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     }
     out.media.push_back(m);
   }
+  // ---- features in use (shade kernel specialisation) ----------------------------------------------------
+  out.spec_bits = 0;
+  if (!out.media.empty()) out.spec_bits |= SPEC_MEDIA;
+  for (const DMedium& m : out.media) {
+    if (m.cls_fast & 0x200) out.spec_bits |= SPEC_BOXSCAN;
+    if (!(m.cls_fast & 0x100)) out.spec_bits |= SPEC_GENERIC_MEDIA;
+  }
+  if (!out.lights.empty()) out.spec_bits |= SPEC_LIGHTS;
+  for (int i = 0; i < out.n_surface_prims; i++) {
+    const int4& info = out.prim_info[i];
+    if (info.y >= 0 && info.y < (int)out.materials.size() && out.materials[info.y].needs_uv)
+      out.spec_bits |= (info.x & 0xFF) == PRIM_QUAD ? SPEC_QUAD_UV : SPEC_SPHERE_UV;
+  }
   return RTB_OK;
 }
 

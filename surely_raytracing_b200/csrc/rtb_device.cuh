@@ -463,7 +463,7 @@ RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded 
 // BOXSCAN: compile the single-scan path for quad-only boundaries in.  The wavefront shade kernel instantiates
 // both and picks per scene: the extra code costs the sphere-media headline scene (c4) 0.9 % through register
 // allocation alone, and gains the box-media scene (c3) 32 %.
-template <bool BOXSCAN = true>
+template <bool BOXSCAN = true, bool GENERIC = true>
 RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, double& t1, double& t2) {
   if (!medium_line_cull(m, r)) return false;
   if (m.cls_fast & 0x100) {
@@ -488,6 +488,9 @@ RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, do
     }
     // degenerate (zero direction ...): fall through to the generic probes
   }
+  // (a scene whose media are all single static spheres never gets past this point with a finite root1: the
+  //  generic probes would return +inf for the degenerate rays too, so their code can be compiled out)
+  if (!GENERIC) return false;
   if (BOXSCAN && (m.cls_fast & 0x200)) {
     // boundary = quads only (a make_box): a quad's plane distance and inside test do not depend on the probe
     // interval, so ONE scan serves both probes of constant_medium.rs:46-55.  Probe 1 returns the smallest
@@ -515,7 +518,7 @@ RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, do
 }
 
 // returns the event parameter t (or +inf) for medium `mi`, given the closest surface so far
-template <bool BOXSCAN = true>
+template <bool BOXSCAN = true, bool GENERIC = true>
 RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, double tmin, double tmax, float U) {
   const float log_u = logf(U);  // U = 0 -> -inf -> hit_distance +inf: no event
   {  // the shortcut below, first in fp32 with a wide margin (most rays leave here)
@@ -536,7 +539,7 @@ RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, dou
     if (hit_distance > bound * (1. + 1e-9) + 1e-12) return RTB_INF;
   }
   double t1, t2;
-  if (!medium_interval<BOXSCAN>(S, m, r, t1, t2)) return RTB_INF;
+  if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2)) return RTB_INF;
   if (t1 < tmin) t1 = tmin;   // :58-60
   if (t2 > tmax) t2 = tmax;   // :61-63
   if (t1 >= t2) return RTB_INF;
@@ -573,7 +576,7 @@ RTB_DEV bool medium_precheck(const DMedium& m, double ox, double oy, double oz, 
   return tn <= fmaf(fabsf(tf), 2e-6f, tf) + 1e-30f;
 }
 
-template <bool BOXSCAN = true>
+template <bool BOXSCAN = true, bool GENERIC = true>
 RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, double oy, double oz, float dx, float dy, float dz,
                                  double time, double tmin, double tmax, float U) {
   if (!medium_precheck(m, ox, oy, oz, dx, dy, dz, tmin, tmax, U)) return RTB_INF;
@@ -581,7 +584,7 @@ RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, d
   r.ox = ox; r.oy = oy; r.oz = oz;
   r.dx = (double)dx; r.dy = (double)dy; r.dz = (double)dz;
   r.time = time;
-  return medium_event<BOXSCAN>(S, m, r, tmin, tmax, U);
+  return medium_event<BOXSCAN, GENERIC>(S, m, r, tmin, tmax, U);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -854,7 +857,8 @@ RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st)
 // material response at the event; returns false when the path ends (contribution added to L)
 // LIGHTS = false compiles the light-list sampler (HittablePDF: f64 probes per light) out: the wavefront shade
 // kernel instantiates it for scenes whose light list is empty (what render_par passes, F2).
-template <bool LIGHTS = true>
+// QUAD_UV / SPHERE_UV = false compile the (u, v) evaluation of that primitive kind out (no material reads it).
+template <bool LIGHTS = true, bool QUAD_UV = true, bool SPHERE_UV = true>
 RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb,
                    DStats* st, bool stats) {
   const Ray& r = ps.ray;
@@ -882,7 +886,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
       const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
       front = ddot(r.dx, r.dy, r.dz, n01.x, n01.y, n2d.x) < 0.;  // set_face_normal  hittable.rs:22-37
       n = v3((float)n01.x, (float)n01.y, (float)n2d.x);
-      if (needs_uv) {
+      if (QUAD_UV && needs_uv) {
         double ta = ev.a, tb = ev.b;
         if (!ev.have_ab) {
           ta = tb = 0.;  // wavefront hit records carry only (t, id): re-evaluate Quad::hit for alpha/beta
@@ -904,7 +908,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
       const float inv_r = fast_rcp((float)c2r.y);
       n = v3((float)ex * inv_r, (float)ey * inv_r, (float)ez * inv_r);
       front = (r.dx * ex + r.dy * ey + r.dz * ez) * c2r.y < 0.;  // sign of d.n with n = e / r (a negative radius flips it)
-      if (needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105); f64 like get_sphere_uv
+      if (SPHERE_UV && needs_uv) {  // uv live in object space: undo the baked rotate_y (transform.rs:85-105); f64 like get_sphere_uv
         const double inv_r64 = 1. / c2r.y;
         const double nx = ex * inv_r64, ny = ey * inv_r64, nz = ez * inv_r64;
         const double2 cs = RTB_LDG(S.xforms + RTB_LDG(S.prim_info + ev.prim).z);
@@ -994,7 +998,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
 }
 RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb, DStats* st,
                    bool stats) {
-  return shade<true>(S, scene_tables(S), ps, ev, Lr, Lg, Lb, st, stats);
+  return shade<true, true, true>(S, scene_tables(S), ps, ev, Lr, Lg, Lb, st, stats);
 }
 
 }  // namespace rtb

@@ -624,11 +624,11 @@ struct ShadeItem {  // what moves through shared memory to the lane that shades 
 //    rejections do not settle it); queueing those (ray, medium) pairs in shared memory and evaluating the
 //    queue densely after a barrier was measured: 18.8 -> 23.1 ms per c4 row (a 4-warp block idles through
 //    the whole f64 chain).  Kept per-lane.
-template <bool MEDIA, bool BOXSCAN>
+template <int SPEC>
 __device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
                                           const uint4& d, double& t, int& id, int info_x) {
   if (d.y == PADDING_PIXEL) return CLS_MISS;
-  if (MEDIA && S.n_media > 0) {
+  if ((SPEC & SPEC_MEDIA) && S.n_media > 0) {
     PathRec p;
     unpack_geom(a, b, c, p);
     unpack_state(d, p);
@@ -636,7 +636,7 @@ __device__ __forceinline__ int wf_resolve(const DScene& S, const Tables& T, cons
     for (int mi = 0; mi < S.n_media; mi++) {
       if ((mi & 3) == 0) u = rand4(S, p.pixel, p.sample, p.bounce, 1u + (uint32_t)(mi >> 2));
       const float U = (mi & 3) == 0 ? u.x : ((mi & 3) == 1 ? u.y : ((mi & 3) == 2 ? u.z : u.w));
-      const double tm = medium_event_lazy<BOXSCAN>(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, t, U);
+      const double tm = medium_event_lazy<(SPEC & SPEC_BOXSCAN) != 0, (SPEC & SPEC_GENERIC_MEDIA) != 0>(S, T.media[mi], p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, (double)p.time, 0.0001, t, U);
       if (tm < t) { t = tm; id = -2 - mi; }
     }
   }
@@ -665,7 +665,7 @@ __device__ __forceinline__ int wf_class_prefix(int cls, const int* class_count) 
 
 // 3. ray_color's match arms for one item (render.rs:271-297): finished paths add their radiance to the image,
 //    survivors return true with the next ray packed into `out`.
-template <bool STATS, bool LIGHTS>
+template <bool STATS, int SPEC>
 __device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, const uint4& a, const uint4& b, const uint4& c,
                                               const uint4& d, double t, int id, int info_x, float4* __restrict__ accum,
                                               RayRec& out, DStats& st) {
@@ -683,7 +683,7 @@ __device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, 
   ev.medium = id <= -2 ? -2 - id : -1;
   ev.info_x = id >= 0 ? info_x : 0;
   float Lr = 0.f, Lg = 0.f, Lb = 0.f;
-  if (shade<LIGHTS>(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
+  if (shade<(SPEC & SPEC_LIGHTS) != 0, (SPEC & SPEC_QUAD_UV) != 0, (SPEC & SPEC_SPHERE_UV) != 0>(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
     p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
     p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
     p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
@@ -721,10 +721,8 @@ __device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict_
   }
 }
 
-// Scene-specialised instantiations (chosen at launch): SPEC bit 0 = the scene has constant media, bit 1 = one of
-// them is bounded by quads only (rtb_device.cuh, medium_interval), bit 2 = the light list is not empty.  Code a
-// scene never runs still costs it registers and instruction-cache misses in this 70 KB kernel.
-enum : int { SPEC_MEDIA = 1, SPEC_BOXSCAN = 2, SPEC_LIGHTS = 4, SPEC_ALL = 7 };
+// Scene-specialised instantiations (chosen at launch from DScene::spec_bits, device_scene.h SPEC_*): code a scene
+// never runs still costs it registers and instruction-cache misses in this 70 KB kernel (c4: +3.7 %).
 template <bool STATS, int SPEC>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
@@ -754,7 +752,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
     it.t = __hiloint2double((int)h.y, (int)h.x); it.id = (int)h.z; it.info_x = (int)h.w;
   }
   __syncthreads();  // counters zeroed
-  if (i < n) cls = wf_resolve<(SPEC & SPEC_MEDIA) != 0, (SPEC & SPEC_BOXSCAN) != 0>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
+  if (i < n) cls = wf_resolve<SPEC>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
   // ---- 2. block-local counting sort by class ---------------------------------------------------------
   int dst = wf_class_slot(cls, lane, class_count);
   __syncthreads();
@@ -767,7 +765,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shad
   DStats st = {0, 0, 0, 0, 0, 0};
   if (tid < n_block) {
     const ShadeItem me = items[tid];
-    alive = wf_shade_item<STATS, (SPEC & SPEC_LIGHTS) != 0>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
+    alive = wf_shade_item<STATS, SPEC>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
   }
   wf_append(Q, rays_out, alive, out, lane);
   if (STATS) {
@@ -869,7 +867,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
       const uint4 h = stage[s].h[tid];
       double t = __hiloint2double((int)h.y, (int)h.x);
       int id = (int)h.z;
-      cls = wf_resolve<true, true>(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
+      cls = wf_resolve<SPEC_ALL>(S, T, stage[s].a[tid], stage[s].b[tid], stage[s].c[tid], stage[s].d[tid], t, id, (int)h.w);
       res_t[tid] = t;
       res_id[tid] = id;
     }
@@ -885,7 +883,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_TMA_MIN_BLOCKS) k_wf_
     if (tid < n_block) {
       const int src = order[tid];
       const uint4 h = stage[s].h[src];
-      alive = wf_shade_item<STATS, true>(S, T, stage[s].a[src], stage[s].b[src], stage[s].c[src], stage[s].d[src], res_t[src], res_id[src],
+      alive = wf_shade_item<STATS, SPEC_ALL>(S, T, stage[s].a[src], stage[s].b[src], stage[s].c[src], stage[s].d[src], res_t[src], res_id[src],
                                    (int)h.w, accum, out, st);
     }
     wf_append(Q, rays_out, alive, out, lane);
@@ -912,15 +910,17 @@ static void launch_shade(const DScene& S, const WFQueues& Q, const RayRec* in, R
     k_wf_shade<true, SPEC_ALL><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
     return;
   }
-  const int spec = (S.n_media > 0 ? SPEC_MEDIA : 0) | (S.has_box_media ? SPEC_BOXSCAN : 0) | (S.n_lights > 0 ? SPEC_LIGHTS : 0);
-  switch (spec) {
-    case 0: launch_shade_spec<0>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-    case SPEC_MEDIA: launch_shade_spec<SPEC_MEDIA>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-    case SPEC_MEDIA | SPEC_BOXSCAN: launch_shade_spec<SPEC_MEDIA | SPEC_BOXSCAN>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-    case SPEC_LIGHTS: launch_shade_spec<SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-    case SPEC_LIGHTS | SPEC_MEDIA: launch_shade_spec<SPEC_LIGHTS | SPEC_MEDIA>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-    default: launch_shade_spec<SPEC_ALL>(S, Q, in, out, d_accum, d_stats, blocks, st); break;
-  }
+  // the smallest instantiation whose features cover the scene's (a superset is always correct)
+  constexpr int kC4 = SPEC_MEDIA | SPEC_SPHERE_UV, kC3 = SPEC_MEDIA | SPEC_BOXSCAN | SPEC_GENERIC_MEDIA;
+  const int need = S.spec_bits & SPEC_ALL;
+  auto covers = [need](int spec) { return (spec & need) == need; };
+  if (covers(0)) launch_shade_spec<0>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else if (covers(SPEC_LIGHTS)) launch_shade_spec<SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else if (covers(kC4)) launch_shade_spec<kC4>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else if (covers(kC3)) launch_shade_spec<kC3>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else if (covers(kC4 | SPEC_LIGHTS)) launch_shade_spec<kC4 | SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else if (covers(kC3 | SPEC_LIGHTS)) launch_shade_spec<kC3 | SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  else launch_shade_spec<SPEC_ALL>(S, Q, in, out, d_accum, d_stats, blocks, st);
 }
 
 // accum.w += number of strata rendered, for every pixel (what one atomicAdd(+1) per finished path would sum to)
