@@ -723,8 +723,10 @@ __device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict_
 
 // Scene-specialised instantiations (chosen at launch from DScene::spec_bits, device_scene.h SPEC_*): code a scene
 // never runs still costs it registers and instruction-cache misses in this 70 KB kernel (c4: +3.7 %).
+// Occupancy: the instantiations without the generic medium probes fit 64 registers with ~60 B of spills and
+// run 8 blocks per SM (c4: 16.5 -> 16.2 ms per row); the others stay at 7 blocks / 72 registers.
 template <bool STATS, int SPEC>
-__global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
+__global__ void __launch_bounds__(WF_SHADE_BLOCK, (SPEC & SPEC_GENERIC_MEDIA) ? WF_SHADE_MIN_BLOCKS : WF_SHADE_MIN_BLOCKS + 1) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
                                                             DStats* __restrict__ stats) {
