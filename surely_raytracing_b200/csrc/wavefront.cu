@@ -5,9 +5,9 @@
 //
 //   k_wf_extend     closest surface hit: persistent warps with dynamic ray     HittableList::hit / BvhNode::hit
 //                   fetch and speculative while-while traversal                hittable.rs:88-109, 216-236
-//   k_wf_resolve    constant-medium events + shading class -> per-class bins   ConstantMedium::hit  constant_medium.rs:41-95
-//   k_wf_shade      emit / scatter / mixture-pdf sample, class-sorted;         ray_color  render.rs:271-297
-//                   survivors are appended (densely) to the next ray queue, finished paths accumulate
+//   k_wf_shade      constant-medium events, block-local sort by shading        ConstantMedium::hit  constant_medium.rs:41-95
+//                   class, emit / scatter / mixture-pdf sample; survivors      ray_color  render.rs:271-297
+//                   are appended (densely) to the next ray queue, finished paths accumulate into the image
 //   k_wf_generate   tops the next queue up with new (pixel, stratum) rays      get_ray  render.rs:218-249
 //
 // Data layout in HBM (DESIGN.md "Queues"): two dense ray queues, each FOUR uint4 PLANES of `capacity`
