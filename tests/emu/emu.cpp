@@ -187,6 +187,35 @@ extern "C" long long emu_slow_rays(void* p, long long s_begin, long long s_end, 
 }
 
 
+// features the flattener found in the scene (device_scene.h SPEC_*), and the leaf-reference codec
+extern "C" int emu_spec_bits(void* p) { return static_cast<Emu*>(p)->host.spec_bits; }
+extern "C" int emu_leaf_roundtrip(int first, int count, int kind_bits) {
+  const int ref = leaf_make(first, count, kind_bits);
+  return ref < 0 && leaf_first(ref) == first && leaf_count(ref) == count && leaf_kind_bits(ref) == kind_bits;
+}
+// every leaf of the BVH2 carries the kind bits of its (single) primitive; returns the number of violations
+extern "C" int emu_check_leaf_refs(void* p) {
+  const Emu* e = static_cast<Emu*>(p);
+  const HostScene& h = e->host;
+  int bad = 0;
+  if (h.n_surface_prims == 0) return 0;
+  for (size_t i = 0; i < h.nodes.size() / 4; i++) {
+    int refs[2];
+    std::memcpy(refs, &h.nodes[4 * i + 3], 8);
+    for (int c = 0; c < 2; c++) {
+      if (refs[c] >= 0) { bad += refs[c] >= (int)(h.nodes.size() / 4); continue; }
+      const int first = leaf_first(refs[c]), count = leaf_count(refs[c]);
+      if (first < 0 || first + count > h.n_surface_prims) { bad++; continue; }
+      const int4 info = h.prim_info[first];
+      const int want = ((info.x & 0xFF) == PRIM_QUAD ? LEAF_KIND_QUAD : 0) | ((info.x & PRIM_FLAG_MOVING) ? LEAF_KIND_MOVING : 0);
+      bad += leaf_kind_bits(refs[c]) != want;
+      const int mat = (info.x >> PRIM_MAT_SHIFT) & 0xFFF;
+      bad += mat != 0 && mat - 1 != info.y;
+    }
+  }
+  return bad;
+}
+
 // ---- alternative tree forms of the wavefront traversal (DScene::qnodes, DScene::nodes4): they must find
 //      exactly the closest hits of the fp32 BVH2 and of a brute-force scan.  Rays as stored in the queues.
 struct QRay { double ox, oy, oz; float dx, dy, dz, time; };

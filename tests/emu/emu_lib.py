@@ -39,6 +39,8 @@ def load():
         lib.emu_medium_interval.argtypes = [vp, C.c_int, vp, i64, vp, vp]
         lib.emu_eval_texture.argtypes = [vp, C.c_int, vp, i64, vp]
         lib.emu_eval_light_pdf.argtypes = [vp, vp, i64, vp]
+        lib.emu_spec_bits.argtypes = [vp]
+        lib.emu_check_leaf_refs.argtypes = [vp]
         lib.emu_check_qnodes.argtypes = [vp, vp, i64, i64, vp]
         lib.emu_check_nodes4.argtypes = [vp, vp, i64, i64, vp]
         _lib = lib
@@ -85,6 +87,12 @@ class EmuScene:
         out = np.zeros((len(uvp), 3))
         self._lib.emu_eval_texture(self._h, texture, _ptr(uvp), len(uvp), _ptr(out))
         return out
+
+    def spec_bits(self):
+        return int(self._lib.emu_spec_bits(self._h))
+
+    def leaf_ref_violations(self):
+        return int(self._lib.emu_check_leaf_refs(self._h))
 
     QRAY_DTYPE = np.dtype([("o", "<f8", 3), ("d", "<f4", 3), ("time", "<f4")])  # a ray as the wavefront queues store it
 

@@ -141,3 +141,33 @@ def test_alternative_trees_find_the_same_closest_hits(cfg):
     for name in ("qnodes", "nodes4"):
         assert res[name]["mismatch_bvh2"] == 0 and res[name]["mismatch_brute"] == 0, (name, res[name])
     assert res["nodes4"]["visits"] < 0.75 * res["nodes4"]["visits_bvh2"]   # the collapse does halve the node steps
+
+
+SPEC = dict(MEDIA=1, BOXSCAN=2, LIGHTS=4, GENERIC_MEDIA=8, QUAD_UV=16, SPHERE_UV=32)
+
+
+@pytest.mark.parametrize("cfg,variant,expected", [
+    ("c1", 0, 0),
+    ("c2", 0, SPEC["LIGHTS"]),
+    ("c3", 0, SPEC["MEDIA"] | SPEC["BOXSCAN"] | SPEC["GENERIC_MEDIA"]),
+    ("c3", 1, SPEC["MEDIA"] | SPEC["BOXSCAN"] | SPEC["GENERIC_MEDIA"] | SPEC["LIGHTS"]),
+    ("c4", 0, SPEC["MEDIA"] | SPEC["SPHERE_UV"]),
+    ("c4", 1, SPEC["MEDIA"] | SPEC["SPHERE_UV"] | SPEC["LIGHTS"]),
+    ("c5", 0, SPEC["LIGHTS"]),
+    ("earth", 0, SPEC["SPHERE_UV"]),
+])
+def test_scene_feature_bits_and_leaf_references(cfg, variant, expected):
+    """The flattener's feature bits pick the shade kernel instantiation (a missing bit would compile code the scene
+    needs OUT, so they are pinned per config), and every BVH leaf reference carries its primitive's kind."""
+    e = EmuScene(BuiltScene(cfg, width=32, spp=4, variant=variant))
+    assert e.spec_bits() == expected, (cfg, variant, e.spec_bits())
+    assert e.leaf_ref_violations() == 0
+
+
+def test_leaf_reference_codec():
+    from tests.emu.emu_lib import load
+    lib = load()
+    for first in (0, 1, 3406, (1 << 26) - 1):
+        for count in (1, 2, 4, 8):
+            for kind in (0, 1, 2, 3):
+                assert lib.emu_leaf_roundtrip(first, count, kind) == 1
