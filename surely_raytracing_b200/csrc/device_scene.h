@@ -147,6 +147,7 @@ struct DScene {
   float grid_cell[3];
   int use_qnodes;  // wavefront extend traverses qnodes (else nodes)
   int use_bvh4;    // wavefront extend traverses nodes4
+  int multi_leaf;  // some BVH leaf holds more than one primitive (only with RTB_BVH_LEAF > 1)
   int spec_bits;   // SPEC_* features the scene uses: the wavefront shade kernel picks the smallest instantiation covering them
   DCamera cam;
 };

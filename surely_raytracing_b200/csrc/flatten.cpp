@@ -516,6 +516,8 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   if (B.surfaces.size() >= (size_t)1 << 26) { err = "more than 2^26 surface primitives (leaf references hold 26 index bits)"; return RTB_ERR_UNSUPPORTED; }
   lap("bvh build");
   out.bvh_depth = bvh.max_depth;
+  out.multi_leaf = 0;
+  for (const BuildNode& bn : bvh.nodes) out.multi_leaf |= (bn.left < 0 && bn.count > 1) ? 1 : 0;
   for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
   out.n_surface_prims = (int)B.surfaces.size();
 

@@ -238,7 +238,8 @@ constexpr int TRAV_DONE = 0x7FFFFFFF;
 //   NODES_BVH2  the 64-byte fp32 nodes;
 //   NODES_Q     the 32-byte quantised nodes (rtb_device.cuh, slab_box_q; opt-in, DScene::use_qnodes);
 //   NODES_BVH4  every other level collapsed (DScene::use_bvh4): half the dependent steps per ray.
-enum : int { NODES_BVH2 = 0, NODES_Q = 1, NODES_BVH4 = 2 };
+//   NODES_BVH2_MULTI  the BVH2 with leaves of several primitives (RTB_BVH_LEAF > 1): the generic leaf loop compiled in.
+enum : int { NODES_BVH2 = 0, NODES_Q = 1, NODES_BVH4 = 2, NODES_BVH2_MULTI = 3 };
 template <bool STATS, int NODES>
 __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
                                                                const RayRec* __restrict__ rays_in,
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, WF_EXTEND_MIN_BLOCKS) k_wf_ex
     r.ox = rox; r.oy = roy; r.oz = roz;
     r.dx = (double)rdx; r.dy = (double)rdy; r.dz = (double)rdz; r.time = (double)rtime;
     while (leaf < 0) {
-      const int count = test_leaf(S, leaf, r, 0.0001, best);
+      const int count = test_leaf<NODES == NODES_BVH2_MULTI>(S, leaf, r, 0.0001, best);
       if (STATS) st_prims += (unsigned long long)count;
       leaf = 0;
       if (node < 0) {
@@ -962,6 +963,11 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[1], k_wf_extend<true, NODES_Q>, WF_EXTEND_BLOCK, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[2], k_wf_extend<false, NODES_BVH4>, WF_EXTEND_BLOCK, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r[3], k_wf_extend<true, NODES_BVH4>, WF_EXTEND_BLOCK, 0);
+    int m[2] = {0, 0};
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m[0], k_wf_extend<false, NODES_BVH2_MULTI>, WF_EXTEND_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m[1], k_wf_extend<true, NODES_BVH2_MULTI>, WF_EXTEND_BLOCK, 0);
+    for (int k = 0; k < 2; k++)
+      if (m[k] > 0 && m[k] < ctx->extend_blocks_per_sm[k]) ctx->extend_blocks_per_sm[k] = m[k];
     for (int k = 0; k < 4; k++)
       if (r[k] > 0 && r[k] < ctx->extend_blocks_per_sm[k & 1]) ctx->extend_blocks_per_sm[k & 1] = r[k];
   }
@@ -1075,7 +1081,10 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         if (collect_stats) k_wf_extend_pool<true><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
         else k_wf_extend_pool<false><<<pool_grid, WF_POOL_BLOCK, 0, u.st>>>(S, u.Q, u.in, pool_scratch, d_stats);
       } else {
-        if (S.use_qnodes) {
+        if (S.multi_leaf) {  // leaves of several primitives: the generic leaf loop, fp32 BVH2 nodes
+          if (collect_stats) k_wf_extend<true, NODES_BVH2_MULTI><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+          else k_wf_extend<false, NODES_BVH2_MULTI><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
+        } else if (S.use_qnodes) {
           if (collect_stats) k_wf_extend<true, NODES_Q><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
           else k_wf_extend<false, NODES_Q><<<extend_grid, WF_EXTEND_BLOCK, 0, u.st>>>(S, u.Q, u.in, d_stats);
         } else if (S.use_bvh4) {

@@ -171,3 +171,21 @@ def test_leaf_reference_codec():
         for count in (1, 2, 4, 8):
             for kind in (0, 1, 2, 3):
                 assert lib.emu_leaf_roundtrip(first, count, kind) == 1
+
+
+def test_multi_primitive_leaves_on_the_host_build(monkeypatch):
+    """RTB_BVH_LEAF > 1: leaves of several primitives go through the generic leaf loop (prim_info read per test)."""
+    monkeypatch.setenv("RTB_BVH_LEAF", "4")
+    monkeypatch.setenv("RTB_BVH_CI", "0.7")
+    b = BuiltScene("c4", width=96, spp=4)
+    e = EmuScene(b)
+    assert e.leaf_ref_violations() == 0
+    rays = orc.OracleScene(b, use_bvh=False).camera_rays()
+    he, hb = e.trace(rays), e.trace(rays, capi.RTB_TRACE_BRUTE_FORCE)
+    assert (hb["prim"] == he["prim"]).all() and np.array_equal(hb["t"], he["t"])
+    monkeypatch.delenv("RTB_BVH_LEAF")
+    monkeypatch.delenv("RTB_BVH_CI")
+    e1 = EmuScene(b)
+    assert e.info.n_bvh_nodes < 0.7 * e1.info.n_bvh_nodes
+    h1 = e1.trace(rays)
+    assert (h1["prim"] == he["prim"]).all() and np.array_equal(h1["t"], he["t"])

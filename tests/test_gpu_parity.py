@@ -173,6 +173,23 @@ def test_opt_in_tree_forms_give_the_same_image(cfg, env, monkeypatch):
         assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
 
 
+def test_multi_primitive_leaves_give_the_same_image(monkeypatch):
+    """RTB_BVH_LEAF > 1 (a tuning knob of the builder) makes leaves of several primitives: the extend kernel then
+    runs its generic-leaf instantiation.  Same closest hits, same image; fewer nodes, more primitive tests."""
+    b = BuiltScene("c4", width=160, spp=16)
+    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    monkeypatch.setenv("RTB_BVH_LEAF", "4")
+    monkeypatch.setenv("RTB_BVH_CI", "0.7")
+    g = Scene(b)
+    alt, st = g.render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert st["segments"] == st_ref["segments"] and st["prim_tests"] > 1.5 * st_ref["prim_tests"]
+    assert st["node_visits"] < st_ref["node_visits"]
+    assert np.allclose(alt, ref, rtol=1e-5, atol=1e-4)
+    rays = g.camera_rays()[::7]
+    hb, hg = g.trace(rays, capi.RTB_TRACE_BRUTE_FORCE), g.trace(rays)
+    assert (hb["prim"] == hg["prim"]).all() and np.array_equal(hb["t"], hg["t"])
+
+
 def test_tma_staged_shade_kernel_gives_the_same_image(monkeypatch):
     """The opt-in persistent shade kernel (cp.async.bulk tiles on an mbarrier, index sort) is the same
     computation as the default one: same paths, same segments, same image up to fp32 atomic order --
