@@ -213,6 +213,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   D.use_bvh4 = h.use_bvh4;
   D.spec_bits = h.spec_bits;
   D.multi_leaf = h.multi_leaf;
+  D.defer_ok = h.defer_ok;
   D.n_materials = (int)h.materials.size();
   D.n_textures = (int)h.textures.size();
   D.bvh_depth = h.bvh_depth;

@@ -55,7 +55,8 @@ enum : int { SPEC_MEDIA = 1,        // constant media present
              SPEC_GENERIC_MEDIA = 8,  // a medium whose boundary is not one static sphere (generic boundary probes)
              SPEC_QUAD_UV = 16,     // a quad whose material reads (u, v)
              SPEC_SPHERE_UV = 32,   // a sphere whose material reads (u, v)
-             SPEC_ALL = 63 };
+             SPEC_TEXTURES = 64,    // a texture that is not a solid colour (checker / image / noise evaluation)
+             SPEC_ALL = 127 };
 
 constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
 constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf
@@ -147,6 +148,7 @@ struct DScene {
   float grid_cell[3];
   int use_qnodes;  // wavefront extend traverses qnodes (else nodes)
   int use_bvh4;    // wavefront extend traverses nodes4
+  int defer_ok;    // every non-solid texture hangs off a Lambertian surface material (classes LAMBERT_TEX / NOISE)
   int multi_leaf;  // some BVH leaf holds more than one primitive (only with RTB_BVH_LEAF > 1)
   int spec_bits;   // SPEC_* features the scene uses: the wavefront shade kernel picks the smallest instantiation covering them
   DCamera cam;

@@ -705,6 +705,20 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     if (!(m.cls_fast & 0x100)) out.spec_bits |= SPEC_GENERIC_MEDIA;
   }
   if (!out.lights.empty()) out.spec_bits |= SPEC_LIGHTS;
+  for (const DTexture& t : out.textures)
+    if (t.kind != TEX_SOLID) out.spec_bits |= SPEC_TEXTURES;
+  // deferred shading of the textured classes (wavefront.cu, k_wf_shade_rare) needs every non-solid texture to hang
+  // off a Lambertian SURFACE material: then "class LAMBERT_TEX / NOISE" and "evaluates a texture" are the same set
+  out.defer_ok = 1;
+  auto root_solid = [&](int mat) {
+    const DMaterial& m = out.materials[mat];
+    const bool textured = m.kind == MAT_LAMBERTIAN || m.kind == MAT_DIFFUSE_LIGHT || m.kind == MAT_ISOTROPIC;
+    return !textured || out.textures[m.texture].kind == TEX_SOLID;
+  };
+  for (size_t i = 0; i < out.materials.size(); i++)
+    if (!root_solid((int)i) && out.materials[i].kind != MAT_LAMBERTIAN) out.defer_ok = 0;
+  for (const DMedium& m : out.media)
+    if (!root_solid(m.material)) out.defer_ok = 0;
   for (int i = 0; i < out.n_surface_prims; i++) {
     const int4& info = out.prim_info[i];
     if (info.y >= 0 && info.y < (int)out.materials.size() && out.materials[info.y].needs_uv)

@@ -22,6 +22,7 @@ struct HostScene {
   std::vector<float4> nodes4;       // 8 per BVH4 node (collapsed from `nodes`)
   int use_bvh4 = 0;
   int use_qnodes = 0;
+  int defer_ok = 0;                 // non-solid textures are reached through Lambertian surface materials only
   int multi_leaf = 0;               // some BVH leaf holds more than one primitive
   int spec_bits = 0;                // SPEC_* features in use (device_scene.h)               // the grid inflates the boxes by < 3 % (surface-area measure): extend uses qnodes
   std::vector<double> prims;        // PRIM_DOUBLES per primitive (BVH order; surfaces, then boundaries)

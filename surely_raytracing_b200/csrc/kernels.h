@@ -20,6 +20,7 @@ struct WavefrontContext {   // per-scene host state of the wavefront driver
   int extend_blocks_per_sm[2];
   int pool_blocks_per_sm[2];
   int extend_kind;          // 0 = per-lane rays (k_wf_extend), 1 = shared-memory ray pool (k_wf_extend_pool)
+  int defer_rare;           // 1 = textured Lambertian items are shaded by k_wf_shade_rare (dense), the main kernel has no texture code
   int shade_tma;            // 1 = persistent shade kernel with TMA-staged tiles (k_wf_shade_tma)
   int shade_tma_blocks_per_sm;
   int n_sub;                // sub-pipelines (streams) the stratum range is split over

@@ -628,7 +628,13 @@ RTB_DEV float perlin_turb(const DScene& S, int table, double px, double py, doub
   return fabsf(accum);
 }
 
+// TEXTURES = false: every texture of the scene is a solid colour, the checker / image / noise code is compiled out
+template <bool TEXTURES = true>
 RTB_DEV V3 texture_value(const DScene& S, const DTexture* textures, int ti, float u, float v, double px, double py, double pz) {
+  if (!TEXTURES) {
+    const DTexture& t = textures[ti];
+    return v3(t.color[0], t.color[1], t.color[2]);
+  }
   for (int guard = 0; guard < 16; guard++) {
     const DTexture& t = textures[ti];
     if (t.kind == TEX_SOLID) return v3(t.color[0], t.color[1], t.color[2]);  // texture.rs:44-46
@@ -657,7 +663,7 @@ RTB_DEV V3 texture_value(const DScene& S, const DTexture* textures, int ti, floa
   return v3(0.f, 0.f, 0.f);
 }
 RTB_DEV V3 texture_value(const DScene& S, int ti, float u, float v, double px, double py, double pz) {
-  return texture_value(S, S.textures, ti, u, v, px, py, pz);
+  return texture_value<true>(S, S.textures, ti, u, v, px, py, pz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -860,7 +866,7 @@ RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st)
 // LIGHTS = false compiles the light-list sampler (HittablePDF: f64 probes per light) out: the wavefront shade
 // kernel instantiates it for scenes whose light list is empty (what render_par passes, F2).
 // QUAD_UV / SPHERE_UV = false compile the (u, v) evaluation of that primitive kind out (no material reads it).
-template <bool LIGHTS = true, bool QUAD_UV = true, bool SPHERE_UV = true>
+template <bool LIGHTS = true, bool QUAD_UV = true, bool SPHERE_UV = true, bool TEXTURES = true>
 RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb,
                    DStats* st, bool stats) {
   const Ray& r = ps.ray;
@@ -924,7 +930,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
   const DMaterial& m = T.materials[mat_id];
   if (m.kind == MAT_DIFFUSE_LIGHT) {  // emitted: front face only; never scatters (Q16)  material.rs:210-221
     if (front) {
-      const V3 e = texture_value(S, T.textures, m.texture, tu, tv, px, py, pz);
+      const V3 e = texture_value<TEXTURES>(S, T.textures, m.texture, tu, tv, px, py, pz);
       Lr += ps.bx * e.x; Lg += ps.by * e.y; Lb += ps.bz * e.z;
     }
     return false;
@@ -958,7 +964,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
   } else {
     // PdfPtr arm  src/render.rs:278-293: MixturePDF(HittablePDF(lights), material pdf)  pdf.rs:102-127
-    const V3 atten = texture_value(S, T.textures, m.texture, tu, tv, px, py, pz);
+    const V3 atten = texture_value<TEXTURES>(S, T.textures, m.texture, tu, tv, px, py, pz);
     const bool lambert = m.kind == MAT_LAMBERTIAN;
     Onb uvw;
     if (lambert) uvw = onb_from_w(n);  // CosinePDF::new  pdf.rs:60-66
@@ -1000,7 +1006,7 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
 }
 RTB_DEV bool shade(const DScene& S, PathState& ps, const Event& ev, float& Lr, float& Lg, float& Lb, DStats* st,
                    bool stats) {
-  return shade<true, true, true>(S, scene_tables(S), ps, ev, Lr, Lg, Lb, st, stats);
+  return shade<true, true, true, true>(S, scene_tables(S), ps, ev, Lr, Lg, Lb, st, stats);
 }
 
 }  // namespace rtb

@@ -35,7 +35,7 @@ struct WFCounters {
   int n_in;           // rays in the current queue
   int n_out;          // rays appended to the next queue (survivors, then regenerated paths)
   int extend_cursor;  // dynamic-fetch cursor of k_wf_extend
-  int pad0;
+  int n_deferred;     // queue positions the shade kernel left to k_wf_shade_rare this iteration
   unsigned long long next_path;    // camera paths started so far
   unsigned long long total_paths;  // to start in this render call (padded tiles included)
   unsigned long long segments;     // sum of n_in over iterations
@@ -49,6 +49,7 @@ struct WFQueues {
   RayRec* rays_a;
   RayRec* rays_b;
   HitRec* hits;
+  int* deferred;      // queue positions of deferred items (see k_wf_shade_rare)
   WFCounters* c;
   int capacity;
 };
@@ -126,7 +127,7 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { __stcs(p, 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t queue_bytes(int64_t n) {
-  return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up(sizeof(WFCounters));
+  return 2 * align_up(n * sizeof(RayRec)) + align_up(n * sizeof(HitRec)) + align_up(n * sizeof(int)) + align_up(sizeof(WFCounters));
 }
 // traversal stacks of the pool extend kernel: one int[WF_POOL_STACK] per pool entry of every resident warp
 constexpr int WF_POOL_MAX_BLOCKS_PER_SM = 12;
@@ -141,6 +142,7 @@ static WFQueues carve(void* ws, int64_t n) {
   q.rays_a = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
   q.rays_b = reinterpret_cast<RayRec*>(take(n * sizeof(RayRec)));
   q.hits = reinterpret_cast<HitRec*>(take(n * sizeof(HitRec)));
+  q.deferred = reinterpret_cast<int*>(take(n * sizeof(int)));
   q.c = reinterpret_cast<WFCounters*>(take(sizeof(WFCounters)));
   q.capacity = (int)n;
   return q;
@@ -166,6 +168,7 @@ __global__ void k_wf_advance(WFQueues Q) {
   c->segments += (unsigned long long)c->n_in;
   c->n_out = 0;
   c->extend_cursor = 0;
+  c->n_deferred = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,7 +687,8 @@ __device__ __forceinline__ bool wf_shade_item(const DScene& S, const Tables& T, 
   ev.medium = id <= -2 ? -2 - id : -1;
   ev.info_x = id >= 0 ? info_x : 0;
   float Lr = 0.f, Lg = 0.f, Lb = 0.f;
-  if (shade<(SPEC & SPEC_LIGHTS) != 0, (SPEC & SPEC_QUAD_UV) != 0, (SPEC & SPEC_SPHERE_UV) != 0>(S, T, ps, ev, Lr, Lg, Lb, &st, STATS)) {
+  if (shade<(SPEC & SPEC_LIGHTS) != 0, (SPEC & SPEC_QUAD_UV) != 0, (SPEC & SPEC_SPHERE_UV) != 0, (SPEC & SPEC_TEXTURES) != 0>(S, T, ps, ev, Lr, Lg,
+                                                                                                                          Lb, &st, STATS)) {
     p.ox = ps.ray.ox; p.oy = ps.ray.oy; p.oz = ps.ray.oz;
     p.dx = (float)ps.ray.dx; p.dy = (float)ps.ray.dy; p.dz = (float)ps.ray.dz;
     p.bx = ps.bx; p.by = ps.by; p.bz = ps.bz;
@@ -726,7 +730,10 @@ __device__ __forceinline__ void wf_append(const WFQueues& Q, RayRec* __restrict_
 // never runs still costs it registers and instruction-cache misses in this 70 KB kernel (c4: +3.7 %).
 // Occupancy: the instantiations without the generic medium probes fit 64 registers with ~60 B of spills and
 // run 8 blocks per SM (c4: 16.5 -> 16.2 ms per row); the others stay at 7 blocks / 72 registers.
-template <bool STATS, int SPEC>
+// DEFER: items of the rare, heavy, textured classes (image / Perlin Lambertians: 0.8 % of c4's items, but 8 % of this
+// kernel's warp instructions at 5 of 32 lanes, and 20 KB of its code) are not shaded here: their queue positions
+// go to a list that k_wf_shade_rare works off densely, and this instantiation carries no texture code at all.
+template <bool STATS, int SPEC, bool DEFER = false>
 __global__ void __launch_bounds__(WF_SHADE_BLOCK, (SPEC & SPEC_GENERIC_MEDIA) ? WF_SHADE_MIN_BLOCKS : WF_SHADE_MIN_BLOCKS + 1) k_wf_shade(const __grid_constant__ DScene S, WFQueues Q,
                                                             const RayRec* __restrict__ rays_in,
                                                             RayRec* __restrict__ rays_out, float4* __restrict__ accum,
@@ -756,17 +763,38 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, (SPEC & SPEC_GENERIC_MEDIA) ? 
   }
   __syncthreads();  // counters zeroed
   if (i < n) cls = wf_resolve<SPEC>(S, T, it.a, it.b, it.c, it.d, it.t, it.id, it.info_x);
+  if (DEFER) {
+    // a deferred item is a surface hit no medium event came before, so its hit record already says everything
+    const bool defer = (cls == CLS_LAMBERT_TEX || cls == CLS_NOISE) && it.id >= 0;
+    const unsigned dm = __ballot_sync(0xFFFFFFFFu, defer);
+    if (dm) {
+      const int leader = __ffs(dm) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&Q.c->n_deferred, __popc(dm));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (defer) {
+        Q.deferred[base + __popc(dm & ((1u << lane) - 1u))] = i;
+        cls = -1;
+      }
+    }
+  }
   // ---- 2. block-local counting sort by class ---------------------------------------------------------
   int dst = wf_class_slot(cls, lane, class_count);
   __syncthreads();
   if (cls >= 0) items[dst + wf_class_prefix(cls, class_count)] = it;
   __syncthreads();
   const int n_block = min(WF_SHADE_BLOCK, n - blockIdx.x * WF_SHADE_BLOCK);
+  int n_sorted = n_block;
+  if (DEFER) {
+    n_sorted = 0;
+#pragma unroll
+    for (int k = 0; k < NUM_CLASSES; k++) n_sorted += class_count[k];
+  }
   // ---- 3. shade the item at sorted position `tid` -----------------------------------------------------
   bool alive = false;
   RayRec out;
   DStats st = {0, 0, 0, 0, 0, 0};
-  if (tid < n_block) {
+  if (tid < n_sorted) {
     const ShadeItem me = items[tid];
     alive = wf_shade_item<STATS, SPEC>(S, T, me.a, me.b, me.c, me.d, me.t, me.id, me.info_x, accum, out, st);
   }
@@ -775,6 +803,30 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, (SPEC & SPEC_GENERIC_MEDIA) ? 
     if (st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
     if (tid == 0 && S.n_media > 0) atomicAdd(&stats->medium_probes, (unsigned long long)S.n_media * (unsigned long long)n_block);
   }
+}
+
+// the deferred items of k_wf_shade<.., DEFER = true>: same shading (every feature compiled in), dense lanes
+template <bool STATS>
+__global__ void __launch_bounds__(WF_SHADE_BLOCK) k_wf_shade_rare(const __grid_constant__ DScene S, WFQueues Q,
+                                                                   const RayRec* __restrict__ rays_in, RayRec* __restrict__ rays_out,
+                                                                   float4* __restrict__ accum, DStats* __restrict__ stats) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nd = Q.c->n_deferred, cap = Q.capacity;
+  const Tables T = scene_tables(S);
+  DStats st = {0, 0, 0, 0, 0, 0};
+  for (int base = blockIdx.x * WF_SHADE_BLOCK; base < nd; base += gridDim.x * WF_SHADE_BLOCK) {  // uniform per block
+    bool alive = false;
+    RayRec out;
+    if (base + tid < nd) {
+      const int j = Q.deferred[base + tid];
+      const uint4 a = __ldg(ray_plane(rays_in, cap, 0) + j), b = __ldg(ray_plane(rays_in, cap, 1) + j);
+      const uint4 c = __ldg(ray_plane(rays_in, cap, 2) + j), d = __ldg(ray_plane(rays_in, cap, 3) + j);
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(Q.hits + j));
+      alive = wf_shade_item<STATS, SPEC_ALL>(S, T, a, b, c, d, __hiloint2double((int)h.y, (int)h.x), (int)h.z, (int)h.w, accum, out, st);
+    }
+    wf_append(Q, rays_out, alive, out, lane);
+  }
+  if (STATS && st.nonfinite) atomicAdd(&stats->nonfinite, st.nonfinite);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -907,14 +959,29 @@ static void launch_shade_spec(const DScene& S, const WFQueues& Q, const RayRec* 
                               unsigned blocks, cudaStream_t st) {
   k_wf_shade<false, SPEC><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
 }
-static void launch_shade(const DScene& S, const WFQueues& Q, const RayRec* in, RayRec* out, float4* d_accum, DStats* d_stats,
-                         bool collect_stats, unsigned blocks, cudaStream_t st) {
+template <int SPEC>
+static void launch_shade_defer(const DScene& S, const WFQueues& Q, const RayRec* in, RayRec* out, float4* d_accum, DStats* d_stats,
+                               unsigned blocks, int sms, cudaStream_t st) {
+  k_wf_shade<false, SPEC, true><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
+  const unsigned rare = std::max(1u, std::min(blocks / 16u, (unsigned)(sms * 4)));
+  k_wf_shade_rare<false><<<rare, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
+}
+// returns the number of kernels launched
+static int launch_shade(const DScene& S, const WFQueues& Q, const RayRec* in, RayRec* out, float4* d_accum, DStats* d_stats,
+                        bool collect_stats, unsigned blocks, bool defer_rare, int sms, cudaStream_t st) {
+  constexpr int kTex = SPEC_TEXTURES | SPEC_SPHERE_UV | SPEC_QUAD_UV;
+  if (!collect_stats && defer_rare && S.defer_ok && (S.spec_bits & SPEC_TEXTURES)) {
+    const int need = S.spec_bits & SPEC_ALL & ~kTex;
+    if (need == SPEC_MEDIA) { launch_shade_defer<SPEC_MEDIA>(S, Q, in, out, d_accum, d_stats, blocks, sms, st); return 2; }
+    if (need == (SPEC_MEDIA | SPEC_LIGHTS)) { launch_shade_defer<SPEC_MEDIA | SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, sms, st); return 2; }
+    if (need == 0) { launch_shade_defer<0>(S, Q, in, out, d_accum, d_stats, blocks, sms, st); return 2; }
+  }
   if (collect_stats) {  // the counted passes are not timed: one generic instantiation
     k_wf_shade<true, SPEC_ALL><<<blocks, WF_SHADE_BLOCK, 0, st>>>(S, Q, in, out, d_accum, d_stats);
-    return;
+    return 1;
   }
   // the smallest instantiation whose features cover the scene's (a superset is always correct)
-  constexpr int kC4 = SPEC_MEDIA | SPEC_SPHERE_UV, kC3 = SPEC_MEDIA | SPEC_BOXSCAN | SPEC_GENERIC_MEDIA;
+  constexpr int kC4 = SPEC_MEDIA | SPEC_SPHERE_UV | SPEC_TEXTURES, kC3 = SPEC_MEDIA | SPEC_BOXSCAN | SPEC_GENERIC_MEDIA;
   const int need = S.spec_bits & SPEC_ALL;
   auto covers = [need](int spec) { return (spec & need) == need; };
   if (covers(0)) launch_shade_spec<0>(S, Q, in, out, d_accum, d_stats, blocks, st);
@@ -924,6 +991,7 @@ static void launch_shade(const DScene& S, const WFQueues& Q, const RayRec* in, R
   else if (covers(kC4 | SPEC_LIGHTS)) launch_shade_spec<kC4 | SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st);
   else if (covers(kC3 | SPEC_LIGHTS)) launch_shade_spec<kC3 | SPEC_LIGHTS>(S, Q, in, out, d_accum, d_stats, blocks, st);
   else launch_shade_spec<SPEC_ALL>(S, Q, in, out, d_accum, d_stats, blocks, st);
+  return 1;
 }
 
 // accum.w += number of strata rendered, for every pixel (what one atomicAdd(+1) per finished path would sum to)
@@ -974,6 +1042,7 @@ cudaError_t wavefront_context_create(WavefrontContext* ctx) {
   ctx->pool_blocks_per_sm[0] = ctx->pool_blocks_per_sm[1] = 4;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[0], k_wf_extend_pool<false>, WF_POOL_BLOCK, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pool_blocks_per_sm[1], k_wf_extend_pool<true>, WF_POOL_BLOCK, 0);
+  ctx->defer_rare = env_int("RTB_WF_DEFER_RARE", 1, 0, 1);  // measured on c4: 16.0 -> 15.4 ms shade per row
   ctx->shade_tma = env_int("RTB_WF_SHADE_TMA", 0, 0, 1);
   ctx->shade_tma_blocks_per_sm = 4;
   {
@@ -1101,7 +1170,7 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
         if (collect_stats) k_wf_shade_tma<true><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
         else k_wf_shade_tma<false><<<grid, WF_SHADE_BLOCK, 0, u.st>>>(S, u.Q, u.in, u.out, d_accum, d_stats);
       } else {
-        launch_shade(S, u.Q, u.in, u.out, d_accum, d_stats, collect_stats, shade_blocks, u.st);
+        n_launch += launch_shade(S, u.Q, u.in, u.out, d_accum, d_stats, collect_stats, shade_blocks, ctx.defer_rare != 0, ctx.sms, u.st) - 1;
       }
       if (profile) {
         cudaEventRecord(pe[3], u.st);

@@ -44,6 +44,7 @@ void* emu_scene_create(const RtbSceneDesc* d) {
   D.nodes4 = h.nodes4.data(); D.use_bvh4 = h.use_bvh4;
   D.spec_bits = h.spec_bits;
   D.multi_leaf = h.multi_leaf;
+  D.defer_ok = h.defer_ok;
   for (int a = 0; a < 3; a++) { D.grid_base[a] = h.grid_base[a]; D.grid_inv_cell[a] = h.grid_inv_cell[a]; D.grid_cell[a] = h.grid_cell[a]; }
   D.flags = h.flags; D.seed_lo = (uint32_t)h.seed; D.seed_hi = (uint32_t)(h.seed >> 32);
   D.cam = h.cam;

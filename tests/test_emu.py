@@ -143,18 +143,18 @@ def test_alternative_trees_find_the_same_closest_hits(cfg):
     assert res["nodes4"]["visits"] < 0.75 * res["nodes4"]["visits_bvh2"]   # the collapse does halve the node steps
 
 
-SPEC = dict(MEDIA=1, BOXSCAN=2, LIGHTS=4, GENERIC_MEDIA=8, QUAD_UV=16, SPHERE_UV=32)
+SPEC = dict(MEDIA=1, BOXSCAN=2, LIGHTS=4, GENERIC_MEDIA=8, QUAD_UV=16, SPHERE_UV=32, TEXTURES=64)
 
 
 @pytest.mark.parametrize("cfg,variant,expected", [
-    ("c1", 0, 0),
+    ("c1", 0, SPEC["TEXTURES"]),          # checker ground
     ("c2", 0, SPEC["LIGHTS"]),
     ("c3", 0, SPEC["MEDIA"] | SPEC["BOXSCAN"] | SPEC["GENERIC_MEDIA"]),
     ("c3", 1, SPEC["MEDIA"] | SPEC["BOXSCAN"] | SPEC["GENERIC_MEDIA"] | SPEC["LIGHTS"]),
-    ("c4", 0, SPEC["MEDIA"] | SPEC["SPHERE_UV"]),
-    ("c4", 1, SPEC["MEDIA"] | SPEC["SPHERE_UV"] | SPEC["LIGHTS"]),
+    ("c4", 0, SPEC["MEDIA"] | SPEC["SPHERE_UV"] | SPEC["TEXTURES"]),
+    ("c4", 1, SPEC["MEDIA"] | SPEC["SPHERE_UV"] | SPEC["TEXTURES"] | SPEC["LIGHTS"]),
     ("c5", 0, SPEC["LIGHTS"]),
-    ("earth", 0, SPEC["SPHERE_UV"]),
+    ("earth", 0, SPEC["SPHERE_UV"] | SPEC["TEXTURES"]),
 ])
 def test_scene_feature_bits_and_leaf_references(cfg, variant, expected):
     """The flattener's feature bits pick the shade kernel instantiation (a missing bit would compile code the scene

@@ -190,6 +190,26 @@ def test_multi_primitive_leaves_give_the_same_image(monkeypatch):
     assert (hb["prim"] == hg["prim"]).all() and np.array_equal(hb["t"], hg["t"])
 
 
+def test_deferred_textured_classes_give_the_same_image(monkeypatch):
+    """By default the image / Perlin Lambertian items are shaded by k_wf_shade_rare from a deferred list and the
+    main shade kernel carries no texture code; RTB_WF_DEFER_RARE=0 shades everything in place.  Same paths, same
+    image (fp32 atomic order aside) -- on the scene with both textured spheres, with and without a light list."""
+    for variant in (0, 1):
+        b = BuiltScene("c4", width=200, spp=16, variant=variant)
+        on, st_on = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
+        monkeypatch.setenv("RTB_WF_DEFER_RARE", "0")
+        off, st_off = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
+        monkeypatch.delenv("RTB_WF_DEFER_RARE")
+        assert st_on["kernel_launches"] > st_off["kernel_launches"]      # the extra k_wf_shade_rare per iteration
+        assert np.allclose(on, off, rtol=1e-5, atol=1e-4)
+    # a scene whose only textured material is NOT a plain Lambertian surface must not defer: simple_light's
+    # textures are Perlin spheres + solid lights (defers), two_perlin_spheres too; furnace-like scenes have none
+    b = BuiltScene("two_perlin_spheres", width=96, spp=9)
+    on, _ = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    mega, _ = Scene(b).render(pipeline=capi.PIPELINE_MEGAKERNEL)
+    assert np.allclose(on, mega, rtol=1e-4, atol=1e-3)
+
+
 def test_tma_staged_shade_kernel_gives_the_same_image(monkeypatch):
     """The opt-in persistent shade kernel (cp.async.bulk tiles on an mbarrier, index sort) is the same
     computation as the default one: same paths, same segments, same image up to fp32 atomic order --
