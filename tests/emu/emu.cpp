@@ -191,6 +191,7 @@ extern "C" long long emu_slow_rays(void* p, long long s_begin, long long s_end, 
 
 // features the flattener found in the scene (device_scene.h SPEC_*), and the leaf-reference codec
 extern "C" int emu_spec_bits(void* p) { return static_cast<Emu*>(p)->host.spec_bits; }
+extern "C" int emu_defer_ok(void* p) { return static_cast<Emu*>(p)->host.defer_ok; }
 extern "C" int emu_leaf_roundtrip(int first, int count, int kind_bits) {
   const int ref = leaf_make(first, count, kind_bits);
   return ref < 0 && leaf_first(ref) == first && leaf_count(ref) == count && leaf_kind_bits(ref) == kind_bits;

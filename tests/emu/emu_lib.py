@@ -40,6 +40,7 @@ def load():
         lib.emu_eval_texture.argtypes = [vp, C.c_int, vp, i64, vp]
         lib.emu_eval_light_pdf.argtypes = [vp, vp, i64, vp]
         lib.emu_spec_bits.argtypes = [vp]
+        lib.emu_defer_ok.argtypes = [vp]
         lib.emu_check_leaf_refs.argtypes = [vp]
         lib.emu_check_qnodes.argtypes = [vp, vp, i64, i64, vp]
         lib.emu_check_nodes4.argtypes = [vp, vp, i64, i64, vp]
@@ -90,6 +91,9 @@ class EmuScene:
 
     def spec_bits(self):
         return int(self._lib.emu_spec_bits(self._h))
+
+    def defer_ok(self):
+        return int(self._lib.emu_defer_ok(self._h))
 
     def leaf_ref_violations(self):
         return int(self._lib.emu_check_leaf_refs(self._h))
