@@ -133,7 +133,7 @@ def sort_experiment():
 
 if len(sys.argv) > 1 and sys.argv[1] == "sort":
     sort_experiment()
-elif len(sys.argv) > 1 and sys.argv[1] in ("checkq", "bvh4"):
+elif len(sys.argv) > 1 and sys.argv[1] in ("checkq", "bvh4", "prefilter"):
     pass
 elif __name__ == "__main__":
     main()
@@ -199,3 +199,32 @@ def bvh4():
 
 if len(sys.argv) > 1 and sys.argv[1] == "bvh4":
     bvh4()
+
+
+def prefilter(width=160, cap=32768):
+    build()
+    lib = C.CDLL(str(LIB))
+    lib.emu_scene_create.restype = C.c_void_p
+    lib.sim_collect.restype = C.c_longlong
+    for cfg in ("c4", "c1", "c2", "c3", "c5"):
+        b = BuiltScene(cfg, width=width)
+        h = C.c_void_p(lib.emu_scene_create(b.desc))
+        if cfg == "c4" and (HERE / f"rays_w{width}_c{cap}.npy").exists():
+            rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
+        else:
+            buf = np.zeros(cap * 3, dtype=QRAY)
+            offs = np.zeros(4, dtype=np.int64)
+            n = lib.sim_collect(h, cap, C.c_longlong(0), C.c_longlong(16), 2, 5, buf.ctypes.data_as(C.c_void_p),
+                                C.c_longlong(len(buf)), offs.ctypes.data_as(C.c_void_p))
+            rays = buf[:n]
+        out = np.zeros(8)
+        r = np.ascontiguousarray(rays)
+        lib.sim_prefilter(h, r.ctypes.data_as(C.c_void_p), C.c_longlong(len(r)), out.ctypes.data_as(C.c_void_p))
+        t = out[0]
+        print(f"{cfg}: {int(t)} leaf tests of {len(r)} rays  certain miss {100 * out[1] / t:5.1f} %  certain hit {100 * out[2] / t:5.1f} %  "
+              f"uncertain {100 * out[3] / t:5.2f} %  exact hits {100 * out[5] / t:5.1f} %  VIOLATIONS {int(out[4])}  "
+              f"mean relative width of the t bounds {out[6] / max(out[2], 1):.2e}")
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "prefilter":
+    prefilter()
