@@ -223,7 +223,7 @@ def prefilter(width=160, cap=32768):
         t = out[0]
         print(f"{cfg}: {int(t)} leaf tests of {len(r)} rays  certain miss {100 * out[1] / t:5.1f} %  certain hit {100 * out[2] / t:5.1f} %  "
               f"uncertain {100 * out[3] / t:5.2f} %  exact hits {100 * out[5] / t:5.1f} %  VIOLATIONS {int(out[4])}  "
-              f"mean relative width of the t bounds {out[6] / max(out[2], 1):.2e}")
+              f"mean relative width of the t bounds {out[6] / max(out[2], 1):.2e}  cheap rejects (plane range / discriminant) {100 * out[7] / t:5.1f} %")
 
 
 if len(sys.argv) > 1 and sys.argv[1] == "prefilter":

@@ -422,6 +422,7 @@ extern "C" int sim_extend4(void* p, const QRay* rays, long long n, const Policy*
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr float EPS32 = 5.9604645e-8f;  // 2^-24
+double g_cheap = 0.;  // certain misses decided before the planar coordinates / the square root
 enum { PF_MISS = 0, PF_HIT = 1, PF_UNSURE = 2 };
 
 int prefilter_quad(const double* P, const Ray& r, double tmin, double tmax, float& t_lo, float& t_hi) {
@@ -439,7 +440,7 @@ int prefilter_quad(const double* P, const Ray& r, double tmin, double tmax, floa
   const float t = num / den;
   const float tw = fabsf(t) * rel + 1e-30f + fabsf((float)(1e-13 * (fabs(nx * r.ox) + fabs(ny * r.oy) + fabs(nz * r.oz) + fabs(dpl)))) / fabsf(den);
   t_lo = t - tw; t_hi = t + tw;
-  if ((double)t_hi < tmin || (double)t_lo > tmax) return PF_MISS;
+  if ((double)t_hi < tmin || (double)t_lo > tmax) { g_cheap++; return PF_MISS; }
   // planar hit point relative to q
   const float ex = (float)(r.ox - qx), ey = (float)(r.oy - qy), ez = (float)(r.oz - qz);
   const float hx = ex + t * dx, hy = ey + t * dy, hz = ez + t * dz;
@@ -469,7 +470,7 @@ int prefilter_sphere(const double* P, bool moving, const Ray& r, double tmin, do
   const float hb_err = 8.f * EPS32 * (fabsf(ocx * dx) + fabsf(ocy * dy) + fabsf(ocz * dz));
   const float disc = hb * hb - a * cc;
   const float disc_err = 2.f * fabsf(hb) * hb_err + hb_err * hb_err + 8.f * EPS32 * (hb * hb + fabsf(a * cc));
-  if (disc < -disc_err) return PF_MISS;
+  if (disc < -disc_err) { g_cheap++; return PF_MISS; }
   if (disc <= 4.f * disc_err) return PF_UNSURE;  // grazing
   const float sq = sqrtf(disc);
   const float sq_err = disc_err / sq + 4.f * EPS32 * sq;
@@ -495,6 +496,7 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
   const DScene& S = e->dev;
   const float tmin32 = __double2float_rd(0.0001);
   for (int k = 0; k < 8; k++) out[k] = 0.;
+  g_cheap = 0.;
   for (long long i = 0; i < n; i++) {
     Ray r;
     r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
@@ -543,5 +545,6 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
       node = stack[--sp];
     }
   }
+  out[7] = g_cheap;
   return 0;
 }
