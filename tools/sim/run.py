@@ -133,7 +133,7 @@ def sort_experiment():
 
 if len(sys.argv) > 1 and sys.argv[1] == "sort":
     sort_experiment()
-elif len(sys.argv) > 1 and sys.argv[1] in ("checkq", "bvh4", "prefilter"):
+elif len(sys.argv) > 1 and sys.argv[1] in ("checkq", "bvh4", "prefilter", "candidates"):
     pass
 elif __name__ == "__main__":
     main()
@@ -228,3 +228,32 @@ def prefilter(width=160, cap=32768):
 
 if len(sys.argv) > 1 and sys.argv[1] == "prefilter":
     prefilter()
+
+
+def candidates(width=160, cap=32768):
+    build()
+    lib = C.CDLL(str(LIB))
+    lib.emu_scene_create.restype = C.c_void_p
+    lib.sim_collect.restype = C.c_longlong
+    for cfg in ("c4", "c1", "c2", "c3", "c5"):
+        b = BuiltScene(cfg, width=width)
+        h = C.c_void_p(lib.emu_scene_create(b.desc))
+        if cfg == "c4" and (HERE / f"rays_w{width}_c{cap}.npy").exists():
+            rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
+        else:
+            buf = np.zeros(cap * 3, dtype=QRAY)
+            offs = np.zeros(4, dtype=np.int64)
+            n = lib.sim_collect(h, cap, C.c_longlong(0), C.c_longlong(16), 2, 5, buf.ctypes.data_as(C.c_void_p),
+                                C.c_longlong(len(buf)), offs.ctypes.data_as(C.c_void_p))
+            rays = buf[:n]
+        r = np.ascontiguousarray(rays)
+        for K in (1, 2, 3):
+            out = np.zeros(8)
+            lib.sim_candidates(h, r.ctypes.data_as(C.c_void_p), C.c_longlong(len(r)), K, out.ctypes.data_as(C.c_void_p))
+            nr = out[0]
+            print(f"{cfg} K={K}: rays {int(nr)}  MISMATCHES {int(out[1])}  fallbacks {100 * out[2] / nr:6.3f} %  candidates/ray {out[3] / max(nr - out[2], 1):5.3f}  "
+                  f"rays with >= 2 candidates {100 * out[6] / nr:5.2f} %  node visits/ray {out[4] / nr:6.2f} (exact scheme {out[5] / nr:6.2f})")
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "candidates":
+    candidates()

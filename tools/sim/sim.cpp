@@ -548,3 +548,86 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
   out[7] = g_cheap;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// PROTOTYPE, continued: the whole candidate scheme.  Traverse with the fp32 prefilter only, keeping up to K
+// candidate primitives (certain hits tighten the cull bound to their t_hi, uncertain ones are kept without
+// tightening, candidates whose t_lo lies beyond the bound are dropped); then resolve the candidates with the exact
+// f64 tests.  Rays with more than K live candidates fall back to the exact traversal.  Checked against
+// closest_surface: prim AND t must be identical.  out: 0 rays, 1 mismatches, 2 fallbacks, 3 sum of candidates
+// resolved, 4 node visits (candidate scheme), 5 node visits (exact scheme), 6 rays with >= 2 candidates.
+// ------------------------------------------------------------------------------------------------
+extern "C" int sim_candidates(void* p, const QRay* rays, long long n, int K, double* out) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  const float tmin32 = __double2float_rd(0.0001);
+  for (int k = 0; k < 8; k++) out[k] = 0.;
+  struct Cand { int ref; float t_lo; };
+  for (long long i = 0; i < n; i++) {
+    Ray r;
+    r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
+    r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
+    const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz);
+    Cand cand[8];
+    int nc = 0;
+    bool overflow = false;
+    float bound = __int_as_float(0x7F800000);  // +inf
+    int stack[BVH_STACK], sp = 0, node = 0;
+    double visits = 0;
+    for (;;) {
+      if (node >= 0) {
+        visits++;
+        const float4* N = S.nodes + 4 * (size_t)node;
+        float tn0, tn1;
+        bool h0, h1;
+        slab_box(N[0].x, N[0].y, N[0].z, N[0].w, N[2].x, N[2].y, sr, tmin32, bound, tn0, h0);
+        slab_box(N[1].x, N[1].y, N[1].z, N[1].w, N[2].z, N[2].w, sr, tmin32, bound, tn1, h1);
+        int ch0 = __float_as_int(N[3].x), ch1 = __float_as_int(N[3].y);
+        if (h0 && h1) {
+          if (tn1 < tn0) std::swap(ch0, ch1);
+          stack[sp++] = ch1;
+          node = ch0;
+          continue;
+        }
+        if (h0) { node = ch0; continue; }
+        if (h1) { node = ch1; continue; }
+      } else {
+        const int pi = leaf_first(node), bits = leaf_kind_bits(node);
+        const double* P = reinterpret_cast<const double*>(S.prims + (size_t)pi * PRIM_D2);
+        float t_lo = 0.f, t_hi = 0.f;
+        const int cls = (bits & LEAF_KIND_QUAD) ? prefilter_quad(P, r, 0.0001, (double)bound, t_lo, t_hi)
+                                                : prefilter_sphere(P, (bits & LEAF_KIND_MOVING) != 0, r, 0.0001, (double)bound, t_lo, t_hi);
+        if (cls != PF_MISS) {
+          if (cls == PF_HIT) {
+            if (t_hi < bound) bound = t_hi;
+          } else {
+            t_lo = 0.f;  // uncertain: never pruned, never tightens
+          }
+          int m = 0;
+          for (int k = 0; k < nc; k++)
+            if (cand[k].t_lo <= bound) cand[m++] = cand[k];
+          nc = m;
+          if (nc < K) { cand[nc].ref = node; cand[nc].t_lo = t_lo; nc++; }
+          else overflow = true;
+        }
+      }
+      if (sp == 0) break;
+      node = stack[--sp];
+    }
+    Hit exact;
+    hit_reset(exact);
+    DStats st = {0, 0, 0, 0, 0, 0};
+    closest_surface<true>(S, r, 0.0001, exact, &st);
+    out[0]++;
+    out[4] += visits;
+    out[5] += (double)st.node_visits;
+    if (overflow) { out[2]++; continue; }  // would be retraced exactly
+    Hit best;
+    hit_reset(best);
+    for (int k = 0; k < nc; k++) test_leaf(S, cand[k].ref, r, 0.0001, best);
+    out[3] += nc;
+    out[6] += nc >= 2;
+    if (best.prim != exact.prim || best.t != exact.t) out[1]++;
+  }
+  return 0;
+}
