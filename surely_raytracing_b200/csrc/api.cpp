@@ -159,7 +159,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   // (both leased from the process-wide cache), copied with a single cudaMemcpyAsync.
   {
     struct Part { const void* src; size_t bytes; size_t off; };
-    Part parts[13] = {
+    Part parts[14] = {
         {h.nodes.data(), h.nodes.size() * sizeof(float4), 0},
         {h.prims.data(), h.prims.size() * sizeof(double), 0},
         {h.prim_info.data(), h.prim_info.size() * sizeof(int4), 0},
@@ -173,6 +173,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
         {h.lights.data(), h.lights.size() * sizeof(DLight), 0},
         {h.qnodes.data(), h.qnodes.size() * sizeof(uint4), 0},
         {h.nodes4.data(), h.nodes4.size() * sizeof(float4), 0},
+        {h.pre.data(), h.pre.size() * sizeof(DPre), 0},
     };
     size_t total = 0;
     for (Part& p : parts) { p.off = total; total += (std::max<size_t>(p.bytes, 16) + 255) & ~(size_t)255; }
@@ -201,6 +202,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
     D.lights = reinterpret_cast<const DLight*>(dp + parts[10].off);
     D.qnodes = reinterpret_cast<const uint4*>(dp + parts[11].off);
     D.nodes4 = reinterpret_cast<const float4*>(dp + parts[12].off);
+    D.pre = reinterpret_cast<const DPre*>(dp + parts[13].off);
     s->upload_bytes = total;
   }
   D.n_nodes = (int)h.nodes.size() / 4;
@@ -212,6 +214,7 @@ int rtb_scene_create(const RtbSceneDesc* desc, int device, rtb_scene** out) {
   D.use_qnodes = h.use_qnodes;
   D.use_bvh4 = h.use_bvh4;
   D.spec_bits = h.spec_bits;
+  D.scene_mag = h.scene_mag;
   D.multi_leaf = h.multi_leaf;
   D.defer_ok = h.defer_ok;
   D.n_materials = (int)h.materials.size();

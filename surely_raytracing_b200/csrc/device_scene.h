@@ -10,6 +10,7 @@
 //                                  of a scene-wide grid, rounded outward (one 32 B sector per visit)
 //   prims      double2[8*n_prims]  128 B per primitive in BVH-leaf order, f64, world space (instance
 //                                  transforms baked in); surfaces first, then medium-boundary prims
+//   pre        DPre[n_prims]       64 B per primitive: the quad fields of the conservative fp32 prefilter
 //   prim_info  int4[n_prims]       {kind | flags | class << 16 | (material + 1) << 20, material, xform, canonical id}
 //   xforms     double2[n_xforms]   {cos, sin} of the composed rotate_y of an instance chain (uv only)
 //   media, materials, textures, texels (u8 RGB), perlin tables, lights: small tagged records.
@@ -81,6 +82,17 @@ RTB_HD int leaf_kind_bits(int ref) { return ((~ref) >> 3) & 3; }
 constexpr int PRIM_D2 = 8;
 constexpr int PRIM_DOUBLES = 2 * PRIM_D2;
 
+// prefilter record of a QUAD (64 B, two sectors; zero for spheres): what the conservative fp32 test of the
+// wavefront traversal reads instead of the 96 cold payload bytes u | v | w (rtb_device.cuh, prefilter_quad)
+struct alignas(32) DPre {
+  double qx, qy, qz;   // corner q (f64: o - q cancels)
+  float ax, ay, az;    // A = v x w:  alpha = w . (h x v) = A . h
+  float bx, by, bz;    // B = w x u:  beta  = w . (u x h) = B . h
+  float nx, ny, nz;    // unit normal, fp32
+  float ab1;           // max(|A|_1, |B|_1), rounded up: scales the error bound of alpha / beta
+};
+static_assert(sizeof(DPre) == 64, "DPre is read as one 256-bit f64 load + one 256-bit f32 load");
+
 struct DMaterial {
   int kind;
   int texture;
@@ -131,6 +143,7 @@ struct DScene {
   const float4* nodes4;       // 8 per BVH4 node: every other level of the tree collapsed (wavefront extend)
   const double2* prims;
   const int4* prim_info;
+  const DPre* pre;            // one per primitive (BVH order), see DPre
   const double2* xforms;
   const DMedium* media;
   const DMaterial* materials;
@@ -150,6 +163,7 @@ struct DScene {
   int use_bvh4;    // wavefront extend traverses nodes4
   int defer_ok;    // every non-solid texture hangs off a Lambertian surface material (classes LAMBERT_TEX / NOISE)
   int multi_leaf;  // some BVH leaf holds more than one primitive (only with RTB_BVH_LEAF > 1)
+  float scene_mag; // largest |coordinate| of the scene (primitives, media boundaries, camera): scales the f64 rounding bound of the prefilter
   int spec_bits;   // SPEC_* features the scene uses: the wavefront shade kernel picks the smallest instantiation covering them
   DCamera cam;
 };

@@ -341,6 +341,19 @@ int shading_class(const RtbSceneDesc& d, int material) {
 
 void emit_prim(const RtbSceneDesc& d, HostScene& out, const Baked& b) {
   out.prims.insert(out.prims.end(), b.payload, b.payload + PRIM_DOUBLES);
+  DPre pre{};
+  if (b.kind == PRIM_QUAD) {  // payload: n d | q | u | v | w
+    const double* p = b.payload;
+    const D3 u = {p[7], p[8], p[9]}, v = {p[10], p[11], p[12]}, w = {p[13], p[14], p[15]};
+    const D3 A = cross(v, w), B = cross(w, u);
+    pre.qx = p[4]; pre.qy = p[5]; pre.qz = p[6];
+    pre.ax = (float)A.x; pre.ay = (float)A.y; pre.az = (float)A.z;
+    pre.bx = (float)B.x; pre.by = (float)B.y; pre.bz = (float)B.z;
+    pre.nx = (float)p[0]; pre.ny = (float)p[1]; pre.nz = (float)p[2];
+    const double a1 = std::fabs(A.x) + std::fabs(A.y) + std::fabs(A.z), b1 = std::fabs(B.x) + std::fabs(B.y) + std::fabs(B.z);
+    pre.ab1 = std::nextafterf(round_up(std::max(a1, b1)), INFINITY);
+  }
+  out.pre.push_back(pre);
   const int mat_bits = (b.material >= 0 && b.material <= PRIM_MAT_MAX) ? ((b.material + 1) << PRIM_MAT_SHIFT) : 0;
   out.prim_info.push_back(int4{b.kind | b.flags | (shading_class(d, b.material) << PRIM_CLASS_SHIFT) | mat_bits, b.material, b.xform, b.id});
 }
@@ -507,6 +520,11 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
       for (int a = 0; a < 3; a++) M = std::max(M, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
   for (int a = 0; a < 3; a++) M = std::max(M, std::fabs(out.cam.center[a]));
   const double pad = M * 1e-6;
+  {
+    double mag = M;
+    for (int a = 0; a < 3; a++) mag = std::max(mag, std::fabs(out.cam.center[a]) + std::fabs(out.cam.disk_u[a]) + std::fabs(out.cam.disk_v[a]));
+    out.scene_mag = round_up(mag);
+  }
 
   lap("walk");
   BvhBuilder bvh(B.surfaces);

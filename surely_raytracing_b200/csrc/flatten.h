@@ -27,6 +27,8 @@ struct HostScene {
   int spec_bits = 0;                // SPEC_* features in use (device_scene.h)               // the grid inflates the boxes by < 3 % (surface-area measure): extend uses qnodes
   std::vector<double> prims;        // PRIM_DOUBLES per primitive (BVH order; surfaces, then boundaries)
   std::vector<int4> prim_info;
+  std::vector<DPre> pre;            // one per primitive, same order
+  float scene_mag = 1.f;
   std::vector<double2> xforms;
   std::vector<DMedium> media;
   std::vector<DMaterial> materials;

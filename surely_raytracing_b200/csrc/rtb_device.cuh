@@ -440,6 +440,265 @@ RTB_DEV void closest_surface_brute(const DScene& S, const Ray& r, double tmin, H
 }
 
 // ------------------------------------------------------------------------------------------------
+// Candidate scheme of the wavefront pipeline: the traversal decides NOTHING that could change a result.
+//
+// The f64 reference-order tests above are what holds first-hit ids bit-exact, but inside a traversing warp
+// they run at 5-8 of 32 lanes behind a division and a square root (ncu, profiles/r01b_k_wf_extend_*).  So
+// the traversal only classifies each leaf primitive with a cheap test whose every rounding error is bounded:
+//     PF_MISS    the reference test certainly rejects it (or it certainly lies behind a certain hit),
+//     PF_HIT     the reference test certainly accepts it, with its t inside [t_lo, t_hi],
+//     PF_UNSURE  anything else (edges, grazing rays, near-parallel planes, t_min straddled),
+// keeps the (at most CAND_K) primitives that can still be the closest hit, and the shade stage runs the exact
+// test on those survivors with every lane busy.  More live candidates than slots -> the ray is re-traced by
+// the exact kernel (k_wf_extend_exact).  Same closest hit as closest_surface(), bit for bit: a primitive is
+// only ever dropped when its hit is certainly absent or certainly farther than another certain hit.
+//
+// Arithmetic: fp32 with running error bounds (u = 2^-24; the constants carry >= 2x headroom over the
+// first-order terms, and every "certain" decision is a positive comparison, so NaN/inf fall to UNSURE);
+// only the differences that cancel -- plane distance d - n.o, o - q, o - c, |o-c|^2 - r^2 -- are f64
+// (7 DFMA-class operations per test instead of ~50 plus a division and a square root).  Directions may
+// carry a rounding of their own (primary rays are f64 in the queue): 1 u per component, inside the bounds.
+// ------------------------------------------------------------------------------------------------
+enum : int { PF_MISS = 0, PF_HIT = 1, PF_UNSURE = 2 };
+constexpr float PF_U = 5.9604645e-8f;  // 2^-24
+constexpr int CAND_K = 2;
+constexpr int CAND_OVERFLOW = 1;  // candidate-slot sentinel: "re-trace me exactly" (leaf references are negative)
+
+struct PfRay {
+  double ox, oy, oz;
+  float dx, dy, dz, time;
+  float d1;       // |dx| + |dy| + |dz|
+  float dd;       // d . d
+  float num_err;  // bound of the f64 rounding of d - n.o and o - q for this origin (4e-13 x coordinate magnitude)
+};
+RTB_DEV PfRay pf_ray(double ox, double oy, double oz, float dx, float dy, float dz, float time, float scene_mag) {
+  PfRay r;
+  r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = time;
+  r.d1 = fabsf(dx) + fabsf(dy) + fabsf(dz);
+  r.dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+  r.num_err = 4e-13f * (scene_mag + fabsf((float)ox) + fabsf((float)oy) + fabsf((float)oz));
+  return r;
+}
+
+// 32 bytes of a primitive payload / prefilter record in one load instruction (one L1 wavefront per sector)
+struct D4 { double a, b, c, d; };
+RTB_DEV D4 load_d4(const double2* p) {
+#if defined(__CUDACC__)
+  D4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+  return r;
+#else
+  D4 r;
+  r.a = p[0].x; r.b = p[0].y; r.c = p[1].x; r.d = p[1].y;
+  return r;
+#endif
+}
+// 256-bit global load (sm_100: LDG.E.ENL2.256): one instruction per 32-byte sector.  The L1 data pipe
+// charges a wavefront per load instruction and distinct sector, and the lanes of a traversing warp sit on
+// different nodes -- so a 64-byte node read as 2 x 256 bit costs half the wavefronts of 4 x 128 bit.
+struct alignas(32) F8 { float4 lo, hi; };
+RTB_DEV F8 load_f8(const float4* p) {
+  F8 r;
+#if defined(__CUDACC__)
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+#else
+  r.lo = p[0]; r.hi = p[1];
+#endif
+  return r;
+}
+
+// Quad::hit (src/object.rs:453-490), conservatively.  alpha = w.(h x v) = h.(v x w) =: h.A and
+// beta = w.(u x h) = h.(w x u) =: h.B with A, B from the flattener (DPre); h = (o - q) + t d.
+RTB_DEV int prefilter_quad(const double2* __restrict__ P, const DPre* __restrict__ pre, const PfRay& r, float tmin_lo,
+                           float tmin_hi, float bound, float& t_lo, float& t_hi) {
+  const D4 nd = load_d4(P);  // unit normal, d = n.q
+#if defined(__CUDACC__)
+  const D4 q4 = load_d4(reinterpret_cast<const double2*>(pre));
+  const F8 f = load_f8(reinterpret_cast<const float4*>(pre) + 2);
+  const double qx = q4.a, qy = q4.b, qz = q4.c;
+  const float ax = __int_as_float(__double2loint(q4.d)), ay = __int_as_float(__double2hiint(q4.d));
+  const float az = f.lo.x, bx = f.lo.y, by = f.lo.z, bz = f.lo.w, nx = f.hi.x, ny = f.hi.y, nz = f.hi.z, ab1 = f.hi.w;
+#else
+  const double qx = pre->qx, qy = pre->qy, qz = pre->qz;
+  const float ax = pre->ax, ay = pre->ay, az = pre->az, bx = pre->bx, by = pre->by, bz = pre->bz;
+  const float nx = pre->nx, ny = pre->ny, nz = pre->nz, ab1 = pre->ab1;
+#endif
+  t_lo = tmin_lo; t_hi = 0.f;
+  const float den = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
+  const float den_err = 10.f * PF_U * fmaf(fabsf(nx), fabsf(r.dx), fmaf(fabsf(ny), fabsf(r.dy), fabsf(nz * r.dz)));
+  // near-parallel: the reference's |denom| < 1e-8 rule decides, exactly
+  if (!(fabsf(den) > 1e-7f + 4.f * den_err)) return PF_UNSURE;
+  const float num = (float)(nd.d - fma(nd.c, r.oz, fma(nd.b, r.oy, nd.a * r.ox)));
+  const float inv = fast_rcp(den);
+  const float t = num * inv;
+  const float tw = fmaf(fabsf(t), fmaf(1.5f * den_err, fabsf(inv), 10.f * PF_U), 1.5f * r.num_err * fabsf(inv)) + 1e-30f;
+  t_lo = t - tw; t_hi = t + tw;
+  if (t_hi < tmin_lo || t_lo > bound) return PF_MISS;
+  const float ex = (float)(r.ox - qx), ey = (float)(r.oy - qy), ez = (float)(r.oz - qz);
+  const float hx = fmaf(t, r.dx, ex), hy = fmaf(t, r.dy, ey), hz = fmaf(t, r.dz, ez);
+  const float h_err = fmaf(4.f * PF_U, fabsf(ex) + fabsf(ey) + fabsf(ez) + fabsf(t) * r.d1, tw * r.d1) + r.num_err;
+  const float ab_err = ab1 * fmaf(8.f * PF_U, fabsf(hx) + fabsf(hy) + fabsf(hz), h_err) + 4.f * PF_U;
+  const float a = fmaf(ax, hx, fmaf(ay, hy, az * hz));
+  const float b = fmaf(bx, hx, fmaf(by, hy, bz * hz));
+  if (a < -ab_err || a > 1.f + ab_err || b < -ab_err || b > 1.f + ab_err) return PF_MISS;
+  const bool inside = a > ab_err && a < 1.f - ab_err && b > ab_err && b < 1.f - ab_err;
+  return (inside && t_lo >= tmin_hi) ? PF_HIT : PF_UNSURE;
+}
+
+// Sphere::hit (src/object.rs:145-166), conservatively.  Roots through q = -(hb + sgn(hb) sqrt(disc)), q / a
+// and c / q: no cancellation, so a ray leaving its own sphere sees the root at 0 as ~1e-13, not as ~u |hb|.
+// An UNSURE result carries the smallest t the reference could return in t_lo (used for pruning only).
+RTB_DEV int prefilter_sphere(const double2* __restrict__ P, bool moving, const PfRay& r, float tmin_lo, float tmin_hi,
+                             float bound, float& t_lo, float& t_hi) {
+  const D4 cr = load_d4(P);
+  double cx = cr.a, cy = cr.b, cz = cr.c;
+  if (moving) {  // Sphere::center, the reference's own two roundings (src/object.rs:107-112)
+    const D4 cv = load_d4(P + 2);
+    const double tm = (double)r.time;
+    cx = dadd(cx, dmul(tm, cv.a)); cy = dadd(cy, dmul(tm, cv.b)); cz = dadd(cz, dmul(tm, cv.c));
+  }
+  t_lo = tmin_lo; t_hi = 0.f;
+  const double ocx64 = r.ox - cx, ocy64 = r.oy - cy, ocz64 = r.oz - cz;
+  const float ocx = (float)ocx64, ocy = (float)ocy64, ocz = (float)ocz64;
+  const float cc = (float)fma(-cr.d, cr.d, fma(ocz64, ocz64, fma(ocy64, ocy64, ocx64 * ocx64)));
+  const float rad = (float)cr.d;
+  const float cc_err = 4e-15f * fmaf(2.f * rad, rad, fabsf(cc)) + 1e-30f;  // f64 rounding of |oc|^2 - r^2 (both sides')
+  const float hb = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
+  const float hb_err = 10.f * PF_U * fmaf(fabsf(ocx), fabsf(r.dx), fmaf(fabsf(ocy), fabsf(r.dy), fabsf(ocz * r.dz))) + 1e-30f;
+  const float ac = r.dd * cc;
+  const float disc = fmaf(hb, hb, -ac);
+  const float disc_err = fmaf(2.f * fabsf(hb) + hb_err, hb_err, fmaf(12.f * PF_U, fmaf(hb, hb, fabsf(ac)), r.dd * cc_err));
+  if (disc < -disc_err) return PF_MISS;
+  if (!(disc > 4.f * disc_err)) return PF_UNSURE;  // grazing
+  const float sq = fast_sqrt(disc);
+  const float sq_err = fmaf(0.6f * disc_err, fast_rcp(sq), 4.f * PF_U * sq);
+  const float q = -(hb + copysignf(sq, hb));
+  const float q_err = hb_err + sq_err + 2.f * PF_U * fabsf(q);
+  const float inv_q = fast_rcp(q);
+  const float rq = q_err * fabsf(inv_q);
+  if (!(rq < 0.25f)) return PF_UNSURE;
+  const float ra = q * fast_rcp(r.dd), rb = cc * inv_q;
+  const float wa = fabsf(ra) * fmaf(1.4f, rq, 12.f * PF_U) + 1e-30f;
+  const float wb = fmaf(fabsf(cc), fmaf(1.4f, rq, 12.f * PF_U), 1.4f * cc_err) * fabsf(inv_q) + 1e-30f;
+  const bool neg = q > 0.f;  // hb < 0 (or -0): ra is the FAR root
+  const float r1 = neg ? rb : ra, w1 = neg ? wb : wa, r2 = neg ? ra : rb, w2 = neg ? wa : wb;
+  // reference root selection over (t_min, closest]: the near root if it lies beyond t_min, else the far one
+  if (r1 - w1 > tmin_hi) {
+    t_lo = r1 - w1; t_hi = r1 + w1;
+    return t_lo > bound ? PF_MISS : PF_HIT;
+  }
+  if (r1 + w1 < tmin_lo) {  // near root certainly rejected
+    if (r2 - w2 > tmin_hi) {
+      t_lo = r2 - w2; t_hi = r2 + w2;
+      return t_lo > bound ? PF_MISS : PF_HIT;
+    }
+    if (r2 + w2 < tmin_lo) return PF_MISS;
+    t_lo = r2 - w2;
+    return t_lo > bound ? PF_MISS : PF_UNSURE;
+  }
+  t_lo = r1 - w1;  // t_min straddled: the reference returns r1, r2 or nothing
+  return t_lo > bound ? PF_MISS : PF_UNSURE;
+}
+
+// the (at most CAND_K) leaf references that can still hold the closest hit, each with the smallest t it could have
+struct Cands {
+  int c0, c1;       // 0 = empty slot; CAND_OVERFLOW in c0 = more live candidates than slots
+  float lo0, lo1;
+  float bound;      // smallest t_hi of a certain hit so far (+inf: none): nothing beyond it can be the closest hit
+};
+RTB_DEV void cands_reset(Cands& C) { C.c0 = 0; C.c1 = 0; C.lo0 = 0.f; C.lo1 = 0.f; C.bound = __int_as_float(0x7F800000); }
+RTB_DEV void cands_add(Cands& C, int ref, int cls, float t_lo, float t_hi) {
+  if (cls == PF_MISS || C.c0 == CAND_OVERFLOW) return;
+  if (cls == PF_HIT && t_hi < C.bound) {
+    C.bound = t_hi;
+    if (C.c1 != 0 && C.lo1 > C.bound) C.c1 = 0;
+    if (C.c0 != 0 && C.lo0 > C.bound) { C.c0 = C.c1; C.lo0 = C.lo1; C.c1 = 0; }
+  }
+  if (C.c0 == 0) { C.c0 = ref; C.lo0 = t_lo; }
+  else if (C.c1 == 0) { C.c1 = ref; C.lo1 = t_lo; }
+  else C.c0 = CAND_OVERFLOW;
+}
+
+// classify the primitive(s) of one leaf and update the candidates.  MULTI as in test_leaf.
+template <bool MULTI = true>
+RTB_DEV int prefilter_leaf(const DScene& S, int leaf_ref, const PfRay& r, float tmin_lo, float tmin_hi, Cands& C) {
+  const int first = leaf_first(leaf_ref), count = leaf_count(leaf_ref);
+  float t_lo, t_hi;
+  if (!MULTI || count == 1) {
+    const int bits = leaf_kind_bits(leaf_ref);
+    const double2* P = S.prims + (size_t)first * PRIM_D2;
+    const int cls = (bits & LEAF_KIND_QUAD) ? prefilter_quad(P, S.pre + first, r, tmin_lo, tmin_hi, C.bound, t_lo, t_hi)
+                                            : prefilter_sphere(P, (bits & LEAF_KIND_MOVING) != 0, r, tmin_lo, tmin_hi, C.bound, t_lo, t_hi);
+    cands_add(C, leaf_ref, cls, t_lo, t_hi);
+  } else {  // the leaf as a whole is the candidate: smallest t_lo of its live primitives, certain hits still tighten
+    int leaf_cls = PF_MISS;
+    float leaf_lo = __int_as_float(0x7F800000), leaf_hi = __int_as_float(0x7F800000);
+    for (int i = 0; i < count; i++) {
+      const int info_x = RTB_LDG(S.prim_info + first + i).x;
+      const double2* P = S.prims + (size_t)(first + i) * PRIM_D2;
+      const int cls = ((info_x & 0xFF) == PRIM_QUAD) ? prefilter_quad(P, S.pre + first + i, r, tmin_lo, tmin_hi, C.bound, t_lo, t_hi)
+                                                     : prefilter_sphere(P, (info_x & PRIM_FLAG_MOVING) != 0, r, tmin_lo, tmin_hi, C.bound, t_lo, t_hi);
+      if (cls == PF_MISS) continue;
+      leaf_lo = fminf(leaf_lo, t_lo);
+      if (cls == PF_HIT) { leaf_hi = fminf(leaf_hi, t_hi); leaf_cls = PF_HIT; }
+      else if (leaf_cls == PF_MISS) leaf_cls = PF_UNSURE;
+    }
+    cands_add(C, leaf_ref, leaf_cls, leaf_lo, leaf_hi);
+  }
+  return count;
+}
+
+// exact resolution of the survivors (shade stage; every lane holds a ray): the reference-order f64 tests with the
+// reference's tie rule, on the candidates only.  MULTI as in test_leaf.
+template <bool MULTI = true>
+RTB_DEV void resolve_candidates(const DScene& S, int c0, int c1, const Ray& r, double tmin, Hit& best) {
+  hit_reset(best);
+  if (c0 < 0) test_leaf<MULTI>(S, c0, r, tmin, best);
+  if (c1 < 0) test_leaf<MULTI>(S, c1, r, tmin, best);
+}
+
+// scalar form of the candidate traversal (parity harness of the host build, tools/sim): the wavefront kernel
+// runs the same prefilter_leaf / cands_add inside its speculative loop.  Returns false on overflow.
+template <bool STATS>
+RTB_DEV bool closest_candidates(const DScene& S, const Ray& r, float scene_mag, Cands& C, DStats* st) {
+  const PfRay pr = pf_ray(r.ox, r.oy, r.oz, (float)r.dx, (float)r.dy, (float)r.dz, (float)r.time, scene_mag);
+  const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, pr.dx, pr.dy, pr.dz);
+  const float tmin_lo = __double2float_rd(0.0001), tmin_hi = __double2float_ru(0.0001);
+  cands_reset(C);
+  int stack[BVH_STACK];
+  int sp = 0, node = 0;
+  for (;;) {
+    if (node >= 0) {
+      if (STATS) st->node_visits++;
+      const float4* N = S.nodes + 4 * (size_t)node;
+      const float4 n0 = RTB_LDG(N + 0), n1 = RTB_LDG(N + 1), n2 = RTB_LDG(N + 2), n3 = RTB_LDG(N + 3);
+      float tn0, tn1;
+      bool h0, h1;
+      slab_box(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sr, tmin_lo, C.bound, tn0, h0);
+      slab_box(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sr, tmin_lo, C.bound, tn1, h1);
+      int ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        if (tn1 < tn0) { const int tmp = ch0; ch0 = ch1; ch1 = tmp; }
+        stack[sp++] = ch1;
+        node = ch0;
+        continue;
+      }
+      if (h0) { node = ch0; continue; }
+      if (h1) { node = ch1; continue; }
+    } else {
+      const int count = prefilter_leaf<true>(S, node, pr, tmin_lo, tmin_hi, C);
+      if (STATS) st->prim_tests += (unsigned long long)count;
+      if (C.c0 == CAND_OVERFLOW) return false;
+    }
+    if (sp == 0) break;
+    node = stack[--sp];
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // constant media.  ConstantMedium::hit  src/constant_medium.rs:41-95 (Q17), restated order-
 // independently: the boundary interval comes from two probes over the medium's own boundary
 // primitives; the free-flight event is accepted inside [max(t1,tmin), min(t2, t_closest)].

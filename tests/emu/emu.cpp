@@ -43,6 +43,7 @@ void* emu_scene_create(const RtbSceneDesc* d) {
   D.qnodes = h.qnodes.data(); D.use_qnodes = h.use_qnodes;
   D.nodes4 = h.nodes4.data(); D.use_bvh4 = h.use_bvh4;
   D.spec_bits = h.spec_bits;
+  D.pre = h.pre.data(); D.scene_mag = h.scene_mag;
   D.multi_leaf = h.multi_leaf;
   D.defer_ok = h.defer_ok;
   for (int a = 0; a < 3; a++) { D.grid_base[a] = h.grid_base[a]; D.grid_inv_cell[a] = h.grid_inv_cell[a]; D.grid_cell[a] = h.grid_cell[a]; }
@@ -107,6 +108,39 @@ int emu_trace(void* p, const RtbRay* rays, long long n, unsigned flags, RtbHit* 
     else if (S.n_surface_prims > 0) closest_surface<false>(S, r, rays[i].t_min, best, nullptr);
     complete_hit(S, r, best, hits[i]);
   }
+  return 0;
+}
+
+// the candidate scheme of the wavefront pipeline (closest_candidates -> exact resolution of the survivors, exact
+// re-trace on overflow), ray by ray.  Directions are taken as given (f64, like the queue's primary records);
+// counts[0] = overflows, counts[1] = candidates resolved, counts[2] = rays with two candidates.
+int emu_trace_candidates(void* p, const RtbRay* rays, long long n, RtbHit* hits, unsigned long long* counts3) {
+  const Emu* e = static_cast<Emu*>(p);
+  const DScene& S = e->dev;
+  unsigned long long overflow = 0, resolved = 0, two = 0;
+  for (long long i = 0; i < n; i++) {
+    if (rays[i].t_min != 0.0001) { g_err = "the wavefront harness traces radiance rays: t_min must be 1e-4"; return -1; }
+    Ray r;
+    r.ox = rays[i].origin[0]; r.oy = rays[i].origin[1]; r.oz = rays[i].origin[2];
+    r.dx = rays[i].direction[0]; r.dy = rays[i].direction[1]; r.dz = rays[i].direction[2];
+    r.time = (double)(float)rays[i].time;
+    Hit best;
+    hit_reset(best);
+    if (S.n_surface_prims > 0) {
+      Cands C;
+      const float mag = fmaxf(S.scene_mag, (float)(fabs(r.ox) + fabs(r.oy) + fabs(r.oz)));
+      if (closest_candidates<false>(S, r, mag, C, nullptr)) {
+        resolve_candidates<true>(S, C.c0, C.c1, r, 0.0001, best);
+        resolved += (C.c0 < 0) + (C.c1 < 0);
+        two += C.c1 < 0;
+      } else {
+        overflow++;
+        closest_surface<false>(S, r, 0.0001, best, nullptr);
+      }
+    }
+    complete_hit(S, r, best, hits[i]);
+  }
+  if (counts3) { counts3[0] = overflow; counts3[1] = resolved; counts3[2] = two; }
   return 0;
 }
 

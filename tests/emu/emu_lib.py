@@ -36,6 +36,7 @@ def load():
         lib.emu_scene_info.argtypes = [vp, C.POINTER(capi.RtbSceneInfo)]
         lib.emu_render.argtypes = [vp, i64, i64, vp, vp]
         lib.emu_trace.argtypes = [vp, vp, i64, C.c_uint, vp]
+        lib.emu_trace_candidates.argtypes = [vp, vp, i64, vp, vp]
         lib.emu_medium_interval.argtypes = [vp, C.c_int, vp, i64, vp, vp]
         lib.emu_eval_texture.argtypes = [vp, C.c_int, vp, i64, vp]
         lib.emu_eval_light_pdf.argtypes = [vp, vp, i64, vp]
@@ -76,6 +77,16 @@ class EmuScene:
         hits = np.zeros(len(rays), dtype=capi.HIT_DTYPE)
         self._lib.emu_trace(self._h, _ptr(rays), len(rays), flags, _ptr(hits))
         return hits
+
+    def trace_candidates(self, rays):
+        """closest hits through the candidate scheme (conservative fp32 classification, exact resolution of the
+        survivors); returns (hits, {overflows, resolved, two_candidates})"""
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=capi.HIT_DTYPE)
+        c = np.zeros(3, dtype=np.uint64)
+        if self._lib.emu_trace_candidates(self._h, _ptr(rays), len(rays), _ptr(hits), _ptr(c)) != 0:
+            raise RuntimeError(self._lib.emu_last_error().decode())
+        return hits, {"overflows": int(c[0]), "resolved": int(c[1]), "two_candidates": int(c[2])}
 
     def medium_interval(self, medium, rays):
         rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)

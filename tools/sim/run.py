@@ -223,7 +223,7 @@ def prefilter(width=160, cap=32768):
         t = out[0]
         print(f"{cfg}: {int(t)} leaf tests of {len(r)} rays  certain miss {100 * out[1] / t:5.1f} %  certain hit {100 * out[2] / t:5.1f} %  "
               f"uncertain {100 * out[3] / t:5.2f} %  exact hits {100 * out[5] / t:5.1f} %  VIOLATIONS {int(out[4])}  "
-              f"mean relative width of the t bounds {out[6] / max(out[2], 1):.2e}  cheap rejects (plane range / discriminant) {100 * out[7] / t:5.1f} %")
+              f"mean relative width of the t bounds {out[6] / max(out[2], 1):.2e}")
 
 
 if len(sys.argv) > 1 and sys.argv[1] == "prefilter":
@@ -247,12 +247,12 @@ def candidates(width=160, cap=32768):
                                 C.c_longlong(len(buf)), offs.ctypes.data_as(C.c_void_p))
             rays = buf[:n]
         r = np.ascontiguousarray(rays)
-        for K in (1, 2, 3):
+        for K in (2,):
             out = np.zeros(8)
             lib.sim_candidates(h, r.ctypes.data_as(C.c_void_p), C.c_longlong(len(r)), K, out.ctypes.data_as(C.c_void_p))
             nr = out[0]
             print(f"{cfg} K={K}: rays {int(nr)}  MISMATCHES {int(out[1])}  fallbacks {100 * out[2] / nr:6.3f} %  candidates/ray {out[3] / max(nr - out[2], 1):5.3f}  "
-                  f"rays with >= 2 candidates {100 * out[6] / nr:5.2f} %  node visits/ray {out[4] / nr:6.2f} (exact scheme {out[5] / nr:6.2f})")
+                  f"rays with 2 candidates {100 * out[6] / nr:5.2f} %  node visits/ray {out[4] / nr:6.2f} (exact scheme {out[5] / nr:6.2f})  prefilter tests/ray {out[7] / nr:5.3f}")
 
 
 if len(sys.argv) > 1 and sys.argv[1] == "candidates":

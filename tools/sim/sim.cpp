@@ -411,96 +411,24 @@ extern "C" int sim_extend4(void* p, const QRay* rays, long long n, const Policy*
 
 
 // ------------------------------------------------------------------------------------------------
-// PROTOTYPE for DESIGN.md section 9, item 1: a conservative fp32 primitive test with explicit error bounds.
-// For every leaf test the BVH2 traversal of the collected rays performs, classify the primitive in fp32 as
-//   certain miss | certain hit with t in [t_lo, t_hi] | uncertain
-// and check the classification against the exact f64 reference-order test.  Counts go to out[]:
-//   0 tests, 1 certain miss, 2 certain hit, 3 uncertain, 4 VIOLATIONS (certain miss but exact hit, certain hit but
-//   exact miss, or exact t outside the bounds), 5 exact hits, 6 sum of relative widths of the certain-hit bounds.
-// Only the two f64 differences that cancel (plane distance numerator, |oc|^2 - r^2, o - q, o - c) are taken in
-// f64, as a kernel would: 7 f64 operations per test instead of ~50 plus a division and a square root.
+// Candidate scheme (rtb_device.cuh: prefilter_quad / prefilter_sphere / cands_add), checked on the host build.
+//
+// sim_prefilter: for every leaf test the exact BVH2 traversal of the given rays performs, classify the primitive
+// with the conservative fp32 test and check the classification against the exact f64 reference-order test.
+//   out: 0 tests, 1 certain miss, 2 certain hit, 3 uncertain, 4 VIOLATIONS (certain miss but exact hit, certain hit
+//   but exact miss, or exact t outside [t_lo, t_hi]; an uncertain one whose exact t lies below its t_lo),
+//   5 exact hits, 6 sum of relative widths of the certain-hit windows.
 // ------------------------------------------------------------------------------------------------
-namespace {
-constexpr float EPS32 = 5.9604645e-8f;  // 2^-24
-double g_cheap = 0.;  // certain misses decided before the planar coordinates / the square root
-enum { PF_MISS = 0, PF_HIT = 1, PF_UNSURE = 2 };
-
-int prefilter_quad(const double* P, const Ray& r, double tmin, double tmax, float& t_lo, float& t_hi) {
-  const double nx = P[0], ny = P[1], nz = P[2], dpl = P[3], qx = P[4], qy = P[5], qz = P[6];
-  const float ux = (float)P[7], uy = (float)P[8], uz = (float)P[9], vx = (float)P[10], vy = (float)P[11], vz = (float)P[12];
-  const float wx = (float)P[13], wy = (float)P[14], wz = (float)P[15];
-  const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz;
-  const float num = (float)(dpl - (nx * r.ox + ny * r.oy + nz * r.oz));
-  const float fnx = (float)nx, fny = (float)ny, fnz = (float)nz;
-  const float den = fnx * dx + fny * dy + fnz * dz;
-  const float den_abs = fabsf(fnx * dx) + fabsf(fny * dy) + fabsf(fnz * dz);
-  const float den_err = 8.f * EPS32 * den_abs;
-  if (fabsf(den) <= 1e-7f + 4.f * den_err) return PF_UNSURE;  // near-parallel: let the exact test decide (|denom| < 1e-8 rule)
-  const float rel = den_err / fabsf(den) + 8.f * EPS32;
-  const float t = num / den;
-  const float tw = fabsf(t) * rel + 1e-30f + fabsf((float)(1e-13 * (fabs(nx * r.ox) + fabs(ny * r.oy) + fabs(nz * r.oz) + fabs(dpl)))) / fabsf(den);
-  t_lo = t - tw; t_hi = t + tw;
-  if ((double)t_hi < tmin || (double)t_lo > tmax) { g_cheap++; return PF_MISS; }
-  // planar hit point relative to q
-  const float ex = (float)(r.ox - qx), ey = (float)(r.oy - qy), ez = (float)(r.oz - qz);
-  const float hx = ex + t * dx, hy = ey + t * dy, hz = ez + t * dz;
-  const float h_err = 4.f * EPS32 * (fabsf(ex) + fabsf(ey) + fabsf(ez) + fabsf(t) * (fabsf(dx) + fabsf(dy) + fabsf(dz))) +
-                      tw * fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
-  const float wn = fabsf(wx) + fabsf(wy) + fabsf(wz), vn = fabsf(vx) + fabsf(vy) + fabsf(vz), un = fabsf(ux) + fabsf(uy) + fabsf(uz);
-  const float hn = fabsf(hx) + fabsf(hy) + fabsf(hz);
-  const float a = wx * (hy * vz - hz * vy) + wy * (hz * vx - hx * vz) + wz * (hx * vy - hy * vx);
-  const float b = wx * (uy * hz - uz * hy) + wy * (uz * hx - ux * hz) + wz * (ux * hy - uy * hx);
-  const float a_err = 2.f * wn * vn * (h_err + 8.f * EPS32 * hn), b_err = 2.f * wn * un * (h_err + 8.f * EPS32 * hn);
-  if (a < -a_err || a > 1.f + a_err || b < -b_err || b > 1.f + b_err) return PF_MISS;
-  const bool inside = a > a_err && a < 1.f - a_err && b > b_err && b < 1.f - b_err;
-  const bool in_range = (double)t_lo >= tmin && (double)t_hi <= tmax;
-  return inside && in_range ? PF_HIT : PF_UNSURE;
-}
-
-int prefilter_sphere(const double* P, bool moving, const Ray& r, double tmin, double tmax, float& t_lo, float& t_hi) {
-  double cx = P[0], cy = P[1], cz = P[2];
-  const double rad = P[3];
-  if (moving) { cx += r.time * P[4]; cy += r.time * P[5]; cz += r.time * P[6]; }
-  const double ocx64 = r.ox - cx, ocy64 = r.oy - cy, ocz64 = r.oz - cz;
-  const float ocx = (float)ocx64, ocy = (float)ocy64, ocz = (float)ocz64;
-  const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz;
-  const float cc = (float)(ocx64 * ocx64 + ocy64 * ocy64 + ocz64 * ocz64 - rad * rad);
-  const float a = dx * dx + dy * dy + dz * dz;
-  const float hb = ocx * dx + ocy * dy + ocz * dz;
-  const float hb_err = 8.f * EPS32 * (fabsf(ocx * dx) + fabsf(ocy * dy) + fabsf(ocz * dz));
-  const float disc = hb * hb - a * cc;
-  const float disc_err = 2.f * fabsf(hb) * hb_err + hb_err * hb_err + 8.f * EPS32 * (hb * hb + fabsf(a * cc));
-  if (disc < -disc_err) { g_cheap++; return PF_MISS; }
-  if (disc <= 4.f * disc_err) return PF_UNSURE;  // grazing
-  const float sq = sqrtf(disc);
-  const float sq_err = disc_err / sq + 4.f * EPS32 * sq;
-  const float inv_a = 1.f / a;
-  const float r1 = (-hb - sq) * inv_a, r2 = (sq - hb) * inv_a;
-  const float rw = (hb_err + sq_err) * inv_a;
-  const float w1 = rw + 8.f * EPS32 * fabsf(r1), w2 = rw + 8.f * EPS32 * fabsf(r2);
-  // reference root selection: the near root if tmin < r1 <= tmax, else the far root if in range (and r1 <= tmax)
-  const bool r1_in = (double)(r1 - w1) > tmin && (double)(r1 + w1) <= tmax;
-  const bool r1_out = (double)(r1 + w1) <= tmin || (double)(r1 - w1) > tmax;
-  if (r1_in) { t_lo = r1 - w1; t_hi = r1 + w1; return PF_HIT; }
-  if (!r1_out) return PF_UNSURE;
-  if ((double)(r1 - w1) > tmax) return PF_MISS;  // the far root is even larger
-  const bool r2_in = (double)(r2 - w2) > tmin && (double)(r2 + w2) <= tmax;
-  const bool r2_out = (double)(r2 + w2) <= tmin || (double)(r2 - w2) > tmax;
-  if (r2_in) { t_lo = r2 - w2; t_hi = r2 + w2; return PF_HIT; }
-  return r2_out ? PF_MISS : PF_UNSURE;
-}
-}  // namespace
-
 extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out) {
   const Emu* e = static_cast<Emu*>(p);
   const DScene& S = e->dev;
-  const float tmin32 = __double2float_rd(0.0001);
+  const float tmin_lo = __double2float_rd(0.0001), tmin_hi = __double2float_ru(0.0001);
   for (int k = 0; k < 8; k++) out[k] = 0.;
-  g_cheap = 0.;
   for (long long i = 0; i < n; i++) {
     Ray r;
     r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
     r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
+    const PfRay pr = pf_ray(r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].time, S.scene_mag);
     Hit best;
     hit_reset(best);
     const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz);
@@ -511,8 +439,8 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
         const float4* N = S.nodes + 4 * (size_t)node;
         float tn0, tn1;
         bool h0, h1;
-        slab_box(N[0].x, N[0].y, N[0].z, N[0].w, N[2].x, N[2].y, sr, tmin32, tbest32, tn0, h0);
-        slab_box(N[1].x, N[1].y, N[1].z, N[1].w, N[2].z, N[2].w, sr, tmin32, tbest32, tn1, h1);
+        slab_box(N[0].x, N[0].y, N[0].z, N[0].w, N[2].x, N[2].y, sr, tmin_lo, tbest32, tn0, h0);
+        slab_box(N[1].x, N[1].y, N[1].z, N[1].w, N[2].z, N[2].w, sr, tmin_lo, tbest32, tn1, h1);
         int ch0 = __float_as_int(N[3].x), ch1 = __float_as_int(N[3].y);
         if (h0 && h1) {
           if (tn1 < tn0) std::swap(ch0, ch1);
@@ -523,21 +451,26 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
         if (h0) { node = ch0; continue; }
         if (h1) { node = ch1; continue; }
       } else {
-        const int pi = leaf_first(node), bits = leaf_kind_bits(node);
-        const double* P = reinterpret_cast<const double*>(S.prims + (size_t)pi * PRIM_D2);
-        float t_lo = 0.f, t_hi = 0.f;
-        const double tmax = best.t;
-        const int cls = (bits & LEAF_KIND_QUAD) ? prefilter_quad(P, r, 0.0001, tmax, t_lo, t_hi)
-                                                : prefilter_sphere(P, (bits & LEAF_KIND_MOVING) != 0, r, 0.0001, tmax, t_lo, t_hi);
-        double t, a, b;
-        const bool exact = (bits & LEAF_KIND_QUAD) ? quad_test(S.prims + (size_t)pi * PRIM_D2, r, 0.0001, tmax, t, a, b)
-                                                   : sphere_test(S.prims + (size_t)pi * PRIM_D2, bits & LEAF_KIND_MOVING, r, r.time, 0.0001, tmax, t);
-        out[0]++;
-        out[1 + cls]++;
-        out[5] += exact;
-        if (cls == PF_MISS && exact) out[4]++;
-        if (cls == PF_HIT && (!exact || t < (double)t_lo || t > (double)t_hi)) out[4]++;
-        if (cls == PF_HIT) out[6] += (double)(t_hi - t_lo) / fmax(1e-30, fabs(t));
+        for (int k = 0; k < leaf_count(node); k++) {
+          const int pi = leaf_first(node) + k;
+          const int info_x = S.prim_info[pi].x;
+          const bool quad = (info_x & 0xFF) == PRIM_QUAD;
+          const double2* P = S.prims + (size_t)pi * PRIM_D2;
+          float t_lo = 0.f, t_hi = 0.f;
+          const float inf = __int_as_float(0x7F800000);
+          const int cls = quad ? prefilter_quad(P, S.pre + pi, pr, tmin_lo, tmin_hi, inf, t_lo, t_hi)
+                               : prefilter_sphere(P, (info_x & PRIM_FLAG_MOVING) != 0, pr, tmin_lo, tmin_hi, inf, t_lo, t_hi);
+          double t, a, b;
+          const bool exact = quad ? quad_test(P, r, 0.0001, RTB_INF, t, a, b)
+                                  : sphere_test(P, info_x & PRIM_FLAG_MOVING, r, r.time, 0.0001, RTB_INF, t);
+          out[0]++;
+          out[1 + cls]++;
+          out[5] += exact;
+          if (cls == PF_MISS && exact) out[4]++;
+          if (cls == PF_HIT && (!exact || t < (double)t_lo || t > (double)t_hi)) out[4]++;
+          if (cls == PF_UNSURE && exact && t < (double)t_lo) out[4]++;
+          if (cls == PF_HIT) out[6] += (double)(t_hi - t_lo) / fmax(1e-30, fabs(t));
+        }
         test_leaf(S, node, r, 0.0001, best);
         tbest32 = __double2float_ru(best.t);
       }
@@ -545,88 +478,39 @@ extern "C" int sim_prefilter(void* p, const QRay* rays, long long n, double* out
       node = stack[--sp];
     }
   }
-  out[7] = g_cheap;
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// PROTOTYPE, continued: the whole candidate scheme.  Traverse with the fp32 prefilter only, keeping up to K
-// candidate primitives (certain hits tighten the cull bound to their t_hi, uncertain ones are kept without
-// tightening, candidates whose t_lo lies beyond the bound are dropped); then resolve the candidates with the exact
-// f64 tests.  Rays with more than K live candidates fall back to the exact traversal.  Checked against
-// closest_surface: prim AND t must be identical.  out: 0 rays, 1 mismatches, 2 fallbacks, 3 sum of candidates
-// resolved, 4 node visits (candidate scheme), 5 node visits (exact scheme), 6 rays with >= 2 candidates.
+// sim_candidates: the whole scheme (closest_candidates + resolve_candidates) against closest_surface on the same
+// rays: prim AND t must be identical.  out: 0 rays, 1 mismatches, 2 overflows (re-traced exactly by the kernel),
+// 3 sum of candidates resolved, 4 node visits (candidate scheme), 5 node visits (exact scheme), 6 rays with 2
+// candidates, 7 prefilter tests.
 // ------------------------------------------------------------------------------------------------
 extern "C" int sim_candidates(void* p, const QRay* rays, long long n, int K, double* out) {
+  (void)K;
   const Emu* e = static_cast<Emu*>(p);
   const DScene& S = e->dev;
-  const float tmin32 = __double2float_rd(0.0001);
   for (int k = 0; k < 8; k++) out[k] = 0.;
-  struct Cand { int ref; float t_lo; };
   for (long long i = 0; i < n; i++) {
     Ray r;
     r.ox = rays[i].ox; r.oy = rays[i].oy; r.oz = rays[i].oz;
     r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
-    const SlabRay sr = slab_ray(r.ox, r.oy, r.oz, rays[i].dx, rays[i].dy, rays[i].dz);
-    Cand cand[8];
-    int nc = 0;
-    bool overflow = false;
-    float bound = __int_as_float(0x7F800000);  // +inf
-    int stack[BVH_STACK], sp = 0, node = 0;
-    double visits = 0;
-    for (;;) {
-      if (node >= 0) {
-        visits++;
-        const float4* N = S.nodes + 4 * (size_t)node;
-        float tn0, tn1;
-        bool h0, h1;
-        slab_box(N[0].x, N[0].y, N[0].z, N[0].w, N[2].x, N[2].y, sr, tmin32, bound, tn0, h0);
-        slab_box(N[1].x, N[1].y, N[1].z, N[1].w, N[2].z, N[2].w, sr, tmin32, bound, tn1, h1);
-        int ch0 = __float_as_int(N[3].x), ch1 = __float_as_int(N[3].y);
-        if (h0 && h1) {
-          if (tn1 < tn0) std::swap(ch0, ch1);
-          stack[sp++] = ch1;
-          node = ch0;
-          continue;
-        }
-        if (h0) { node = ch0; continue; }
-        if (h1) { node = ch1; continue; }
-      } else {
-        const int pi = leaf_first(node), bits = leaf_kind_bits(node);
-        const double* P = reinterpret_cast<const double*>(S.prims + (size_t)pi * PRIM_D2);
-        float t_lo = 0.f, t_hi = 0.f;
-        const int cls = (bits & LEAF_KIND_QUAD) ? prefilter_quad(P, r, 0.0001, (double)bound, t_lo, t_hi)
-                                                : prefilter_sphere(P, (bits & LEAF_KIND_MOVING) != 0, r, 0.0001, (double)bound, t_lo, t_hi);
-        if (cls != PF_MISS) {
-          if (cls == PF_HIT) {
-            if (t_hi < bound) bound = t_hi;
-          } else {
-            t_lo = 0.f;  // uncertain: never pruned, never tightens
-          }
-          int m = 0;
-          for (int k = 0; k < nc; k++)
-            if (cand[k].t_lo <= bound) cand[m++] = cand[k];
-          nc = m;
-          if (nc < K) { cand[nc].ref = node; cand[nc].t_lo = t_lo; nc++; }
-          else overflow = true;
-        }
-      }
-      if (sp == 0) break;
-      node = stack[--sp];
-    }
     Hit exact;
     hit_reset(exact);
-    DStats st = {0, 0, 0, 0, 0, 0};
+    DStats st = {0, 0, 0, 0, 0, 0}, sc = {0, 0, 0, 0, 0, 0};
     closest_surface<true>(S, r, 0.0001, exact, &st);
+    Cands C;
+    const bool ok = closest_candidates<true>(S, r, S.scene_mag, C, &sc);
     out[0]++;
-    out[4] += visits;
+    out[4] += (double)sc.node_visits;
     out[5] += (double)st.node_visits;
-    if (overflow) { out[2]++; continue; }  // would be retraced exactly
+    out[7] += (double)sc.prim_tests;
+    if (!ok) { out[2]++; continue; }
     Hit best;
-    hit_reset(best);
-    for (int k = 0; k < nc; k++) test_leaf(S, cand[k].ref, r, 0.0001, best);
-    out[3] += nc;
-    out[6] += nc >= 2;
+    resolve_candidates<true>(S, C.c0, C.c1, r, 0.0001, best);
+    out[3] += (C.c0 < 0) + (C.c1 < 0);
+    out[6] += (C.c1 < 0);
     if (best.prim != exact.prim || best.t != exact.t) out[1]++;
   }
   return 0;
