@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define RTB_OK 0
@@ -133,6 +133,23 @@ typedef struct RtbCamera {
 #define RTB_FLAG_PROPAGATE_NAN 2u /* HEAD-literal: non-finite samples poison the pixel (Q22);   */
                                   /* default: a non-finite / zero-pdf sample contributes 0      */
 
+/* builder arms of the device tree (measured alternatives to the default 64-byte BVH2 with one-primitive leaves) */
+#define RTB_FLAG_BVH4 0x10u        /* traverse the tree with every other level collapsed (4-wide nodes)          */
+#define RTB_FLAG_QNODES 0x20u      /* 32-byte nodes with 16-bit quantised boxes (vetoed where the grid is coarse) */
+#define RTB_FLAG_BVH_LEAF4 0x40u   /* allow leaves of up to 4 primitives                                          */
+#define RTB_FLAG_NO_BOX_SCAN 0x80u /* quad-bounded media: two boundary probes as written instead of one scan      */
+/* The sun term of ray_color is commented out at HEAD (src/render.rs:300-308: `cam.background //+ sun_light`), so
+ * `suns` is accepted and ignored (Q23).  This flag switches the term back on: a miss adds, for every sun,
+ * Sun::_hit (src/object.rs:232-239): albedo if dot(unit(d), direction) > 1 - angular_diameter/180. */
+#define RTB_FLAG_SUN_LIGHT 0x100u
+
+/* Sun::new (reference src/object.rs:223-231) */
+typedef struct RtbSun {
+  double direction[3]; /* as given; normalised by the library like Sun::new does */
+  double albedo[3];
+  double angular_diameter;
+} RtbSun;
+
 typedef struct RtbSceneDesc {
   int32_t abi_version; /* RTB_ABI_VERSION */
   uint32_t flags;
@@ -157,6 +174,10 @@ typedef struct RtbSceneDesc {
   int32_t n_perlins;
 
   RtbCamera camera;
+
+  const RtbSun* suns; /* the `suns: &Vec<Sun>` argument of render_par (src/render.rs:140); see RTB_FLAG_SUN_LIGHT */
+  int32_t n_suns;
+  int32_t reserved;
 } RtbSceneDesc;
 
 /* ---- deterministic-parity harness types -------------------------------------------------- */
@@ -181,6 +202,13 @@ typedef struct RtbHit {
 } RtbHit;
 
 #define RTB_TRACE_BRUTE_FORCE 1u /* linear scan over all primitives instead of the BVH */
+/* Trace through the kernels rtb_render itself runs: the rays are packed into a ray queue, traversed by the
+ * wavefront extend kernel (conservative classification, <= 2 candidates), re-traced exactly where the candidates
+ * overflowed, and resolved by the exact tests as the shade stage does.  t_min must be 1e-4 (radiance rays).
+ * Default: primary records (f64 directions, what get_ray produces).  With RTB_TRACE_SECONDARY the rays travel
+ * as scattered-ray records: the library rounds their directions and time to fp32, as the shade stage's output is. */
+#define RTB_TRACE_WAVEFRONT 2u
+#define RTB_TRACE_SECONDARY 4u
 
 typedef struct RtbSceneInfo {
   int32_t image_width, image_height;
@@ -214,7 +242,22 @@ typedef struct RtbStats {
   uint64_t nonfinite_samples;
   uint64_t kernel_launches;
   double device_ms; /* CUDA-event time of the kernels of this call */
+  uint64_t exact_tests;   /* f64 reference-order primitive tests (wavefront: on candidates, in the shade stage) */
+  uint64_t overflow_rays; /* rays re-traced by the exact kernel because their candidates did not fit the slots  */
+  double stage_ms[3];     /* RTB_OPT_PROFILE only: CUDA-event totals of generate / extend / shade              */
 } RtbStats;
+
+/* per-scene tuning knobs (rtb_scene_set_option); every default is the measured best */
+enum RtbOption {
+  RTB_OPT_WF_CAPACITY = 1,      /* path slots of the wavefront queues (0 = sized by the call; >= 1024)           */
+  RTB_OPT_EXACT_LEAVES = 2,     /* 1: f64 primitive tests inside the traversal (the round-1 extend kernel)       */
+  RTB_OPT_SMEM_TOP = 3,         /* 1: top BVH levels staged in shared memory                                     */
+  RTB_OPT_NO_DEFER_RARE = 4,    /* 1: textured Lambertian items shaded in place                                  */
+  RTB_OPT_EXTEND_BLOCKS = 5,    /* cap of persistent extend blocks per SM (0 = what fits)                        */
+  RTB_OPT_FINISH_BELOW = 6,     /* rays left at which the finishing kernel takes over (-1 default, 0 never)      */
+  RTB_OPT_PROFILE = 7,          /* 1: per-stage CUDA-event totals on stderr; 2: per iteration                    */
+  RTB_OPT_MEGA_BELOW = 8        /* RTB_PIPELINE_DEFAULT renders calls of fewer paths with the megakernel (-1 default) */
+};
 
 typedef struct rtb_scene rtb_scene;
 
@@ -234,13 +277,31 @@ int rtb_scene_info(const rtb_scene* scene, RtbSceneInfo* info);
  * accumulated INTO like the reference's `row[i] = row[i] + color`, Q24). Blocking. */
 int rtb_render(rtb_scene* scene, const RtbRenderParams* params, double* pixels_rgb, RtbStats* stats);
 
-/* Same, but accumulates into a caller-owned DEVICE buffer of w*h float4 (rgb sum, w = sample
- * count) on `cuda_stream` (a cudaStream_t, may be NULL) without synchronising: the multi-GPU
- * driver reduces these buffers with NCCL. `stats` (may be NULL) is only valid after the stream
- * has been synchronised by the caller and rtb_render_stats() has been called. */
-int rtb_render_device(rtb_scene* scene, const RtbRenderParams* params, void* d_accum_rgba,
+/* Same, but accumulates into a caller-owned DEVICE buffer of w*h x 4 uint64 {r, g, b, count} on
+ * `cuda_stream` (a cudaStream_t, may be NULL) without synchronising.  r, g, b are two's-complement
+ * fixed-point sums in units of 2^-32 (RTB_ACCUM_SCALE) added with integer atomics: the buffer does not
+ * depend on the order paths finish in, so a render is bit-reproducible and buffers of disjoint stratum
+ * ranges -- other calls, other GPUs -- add up exactly (reduce them as int64 sums).  count = strata
+ * accumulated per pixel; bit 62 marks a pixel poisoned under RTB_FLAG_PROPAGATE_NAN.
+ * Stats are valid after the stream has been synchronised and rtb_render_stats() has been called. */
+#define RTB_ACCUM_SCALE 4294967296.0
+int rtb_render_device(rtb_scene* scene, const RtbRenderParams* params, void* d_accum_u64x4,
                       void* cuda_stream);
 int rtb_render_stats(rtb_scene* scene, RtbStats* stats);
+/* device accumulation buffer -> host f64 sums, accumulated INTO pixels_rgb like rtb_render does (blocking) */
+int rtb_accum_to_pixels(rtb_scene* scene, const void* d_accum_u64x4, double* pixels_rgb);
+
+/* The reference seam on one multi-GPU box: render_par_lights (src/render.rs:144-216) for the stratum range in
+ * `params`, split into contiguous slices over `n_devices` GPUs (devices[] or, if NULL, 0..n_devices-1): one
+ * host thread, scene copy and stream per GPU, ONE NCCL sum-reduce of the int64 accumulation buffers to the
+ * first device over NVLink, ONE device-to-host copy.  pixels_rgb as in rtb_render; the image does not depend
+ * on n_devices (bit-identical).  stats (may be NULL): sums over devices, device_ms = the slowest device. */
+int rtb_render_multi(const RtbSceneDesc* desc, int n_devices, const int* devices, const RtbRenderParams* params,
+                     double* pixels_rgb, RtbStats* stats);
+
+int rtb_scene_set_option(rtb_scene* scene, int option /* RtbOption */, int64_t value);
+/* frees the idle blocks of the process-wide buffer cache (queues, staging); returns the bytes released */
+int64_t rtb_trim_cache(void);
 
 /* Deterministic closest-hit of `n` host rays against the scene's SURFACES (media are stochastic
  * and ignored here): the parity harness of SURVEY 8(d). Mirrors HittableList::hit
@@ -264,9 +325,15 @@ int rtb_eval_light_pdf(rtb_scene* scene, const double* origin_dir /* n x 6 */, i
                        double* pdf_out);
 
 /* Output stage: write_color (src/color.rs:8-33) on the device:
- * divide by spp, optional exposure (exposure <= 0: none), sRGB OETF, clamp, (256*x) as u8. */
+ * divide by spp, optional exposure (exposure <= 0: none), sRGB OETF, clamp, (256*x) as u8.
+ * `scene` may be NULL (the image of rtb_render_multi): the current CUDA device is used. */
 int rtb_write_color(rtb_scene* scene, const double* pixels_rgb, int64_t n_pixels, double spp,
                     double exposure, uint8_t* rgb8_out);
+/* auto_expose (src/render.rs:325-339): exposure value for write_color from the f64 sums, evaluated on the host
+ * in the reference's own sequential order (a serial f64 sum: any other order moves the last bit). */
+int rtb_auto_expose(const double* pixels_rgb, int64_t n_pixels, double spp, double* exposure_out);
+/* Random123 known-answer hook for the DEVICE copy of Philox4x32-10: ctr_key = n x {c0,c1,c2,c3,k0,k1}, out = n x 4 */
+int rtb_philox(rtb_scene* scene, const uint32_t* ctr_key, int64_t n, uint32_t* out);
 
 #ifdef __cplusplus
 }

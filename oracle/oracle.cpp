@@ -325,6 +325,8 @@ struct Scene {
   Camera cam;
   uint32_t flags = 0;
   uint64_t seed = 0;
+  struct SunRec { Vec3 direction; Color albedo; double limit; };  // Sun  src/object.rs:216-241
+  std::vector<SunRec> suns;
   int n_prims = 0, n_media = 0;
   bool use_bvh = true;
   std::string error;
@@ -954,7 +956,17 @@ Color ray_color(Ctx& C, const Ray& r, int depth) {  // :251-312
   C.S.set_bounce((uint32_t)(sc.cam.max_depth - depth));
   C.cnt.segments++;
   HitRecord rec;
-  if (!hit_object(C, sc.world, r, Interval{0.0001, INF}, rec)) return sc.cam.background;  // :264-270, 308
+  if (!hit_object(C, sc.world, r, Interval{0.0001, INF}, rec)) {  // :264-270, 298-309
+    // HEAD: `cam.background //+ sun_light` -- the sun term is commented out (Q23).  RTB_FLAG_SUN_LIGHT restates the
+    // commented lines :300-306: sun_light = sum over suns of Sun::_hit(r) (object.rs:232-239)
+    Color sun_light(0., 0., 0.);
+    if (sc.flags & RTB_FLAG_SUN_LIGHT) {
+      const Vec3 unit_direction = unit_vector(r.dir);
+      for (const Scene::SunRec& sun : sc.suns)
+        if (dot(unit_direction, sun.direction) > sun.limit) sun_light = sun_light + sun.albedo;
+    }
+    return sc.cam.background + sun_light;
+  }
   const RtbMaterial& mat = sc.mats[rec.mat];
   Color color_from_emission = material_emitted(C, mat, rec);  // :272
   ScatterRecord srec;
@@ -1043,6 +1055,11 @@ int orc_scene_create(const RtbSceneDesc* d, orc_scene** out) {
   Scene& sc = h->sc;
   sc.flags = d->flags;
   sc.seed = d->seed;
+  for (int i = 0; i < d->n_suns; i++) {  // Sun::new  src/object.rs:223-231
+    const RtbSun& u = d->suns[i];
+    sc.suns.push_back(Scene::SunRec{unit_vector(Vec3(u.direction[0], u.direction[1], u.direction[2])),
+                                    Color(u.albedo[0], u.albedo[1], u.albedo[2]), 1. - u.angular_diameter / 180.});
+  }
   sc.objs.resize(d->n_objects);
   for (int i = 0; i < d->n_objects; i++) {
     const RtbObject& s = d->objects[i];
@@ -1342,6 +1359,20 @@ int orc_write_color(const double* pixels_rgb, int64_t n_pixels, double spp, doub
     rgb8_out[i] = rust_f64_as_u8(256. * c);
   }
   return RTB_OK;
+}
+
+// auto_expose  src/render.rs:325-339
+double orc_auto_expose(const double* pixels_rgb, int64_t n_pixels, double samples_per_pixel) {
+  const double medium_weight = 1. / (double)n_pixels;  // 1 / (image_height * image_width)
+  double medium_point = 0.;
+  for (int64_t i = 0; i < n_pixels; i++) {
+    const Color current_color(pixels_rgb[3 * i], pixels_rgb[3 * i + 1], pixels_rgb[3 * i + 2]);
+    const double luminance = dot(Color(0.2126, 0.71516, 0.072169), current_color);
+    medium_point = medium_point + medium_weight * (luminance * luminance);
+  }
+  medium_point = medium_point / (samples_per_pixel * samples_per_pixel);
+  if (medium_point > 0.001) return -std::log(0.6) / std::sqrt(medium_point);
+  return 1.;
 }
 
 }  // extern "C"

@@ -56,6 +56,7 @@ def load():
         lib.orc_sphere_uv.argtypes = [vp, vp]; lib.orc_sphere_uv.restype = None
         lib.orc_philox.argtypes = [vp, vp, vp]; lib.orc_philox.restype = None
         lib.orc_write_color.argtypes = [vp, i64, C.c_double, C.c_double, vp]
+        lib.orc_auto_expose.argtypes = [vp, i64, C.c_double]; lib.orc_auto_expose.restype = C.c_double
         _lib = lib
     return _lib
 
@@ -164,3 +165,9 @@ def write_color(pixels, spp, exposure=0.0):
     out = np.zeros(px.shape, dtype=np.uint8)
     load().orc_write_color(_ptr(px), px.size // 3, float(spp), float(exposure), _ptr(out))
     return out
+
+
+def auto_expose(pixels, spp):
+    """auto_expose (reference src/render.rs:325-339) over f64 pixel sums"""
+    px = np.ascontiguousarray(pixels, dtype=np.float64)
+    return float(load().orc_auto_expose(_ptr(px), px.size // 3, float(spp)))

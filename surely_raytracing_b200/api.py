@@ -40,9 +40,29 @@ class Scene:
         capi.check(self._lib, self._lib.rtb_render(self._h, C.byref(params), _ptr(out), C.byref(stats)), "rtb_render")
         return out, stats.as_dict()
 
+    def set_option(self, option: int, value: int):
+        """rtb_scene_set_option (capi.OPT_*): per-scene tuning knobs / A-B arms"""
+        capi.check(self._lib, self._lib.rtb_scene_set_option(self._h, option, int(value)), "rtb_scene_set_option")
+        return self
+
+    def accum_to_pixels(self, d_accum_ptr: int, out: np.ndarray | None = None) -> np.ndarray:
+        """rtb_accum_to_pixels: a device accumulation buffer (fixed-point u64 x 4) -> += host f64 sums"""
+        h, w = self.info.image_height, self.info.image_width
+        if out is None:
+            out = np.zeros((h, w, 3), dtype=np.float64)
+        capi.check(self._lib, self._lib.rtb_accum_to_pixels(self._h, C.c_void_p(d_accum_ptr), _ptr(out)), "rtb_accum_to_pixels")
+        return out
+
+    def philox(self, ctr_key: np.ndarray) -> np.ndarray:
+        """the device's Philox4x32-10 on n x {c0,c1,c2,c3,k0,k1} (Random123 known-answer hook)"""
+        ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)
+        out = np.zeros((len(ck), 4), dtype=np.uint32)
+        capi.check(self._lib, self._lib.rtb_philox(self._h, _ptr(ck), len(ck), _ptr(out)), "rtb_philox")
+        return out
+
     def render_device(self, d_accum_ptr: int, sample_begin: int, sample_end: int, stream: int = 0,
                       pipeline: int = 0, collect_stats: bool = False):
-        """rtb_render_device: accumulate into a caller-owned device float4 buffer, asynchronously."""
+        """rtb_render_device: accumulate into a caller-owned device buffer of w*h x 4 uint64 (fixed-point sums), asynchronously."""
         params = RtbRenderParams(sample_begin, sample_end, pipeline, 1 if collect_stats else 0)
         capi.check(self._lib, self._lib.rtb_render_device(self._h, C.byref(params), C.c_void_p(d_accum_ptr),
                                                           C.c_void_p(stream)), "rtb_render_device")
@@ -100,3 +120,33 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+def render_multi(built, n_devices: int, sample_begin: int = 0, sample_end: int | None = None, pipeline: int = 0,
+                 devices=None, collect_stats: bool = False, out: np.ndarray | None = None):
+    """rtb_render_multi: the reference seam on the GPUs of one box (one thread + stream per GPU, one NCCL sum-reduce of
+    the int64 accumulation buffers, one device-to-host copy).  Returns (pixels[h,w,3] f64 sums, stats dict)."""
+    lib = capi.load_library()
+    desc = built.desc if hasattr(built, "desc") else built
+    cam = desc.contents.camera
+    h = max(1, int(cam.image_width / cam.aspect_ratio))
+    root = int(np.sqrt(cam.samples_per_pixel))
+    if sample_end is None:
+        sample_end = root * root
+    if out is None:
+        out = np.zeros((h, cam.image_width, 3), dtype=np.float64)
+    params = RtbRenderParams(sample_begin, sample_end, pipeline, 1 if collect_stats else 0)
+    stats = RtbStats()
+    devs = None
+    if devices is not None:
+        devs = (C.c_int * len(devices))(*devices)
+    capi.check(lib, lib.rtb_render_multi(desc, n_devices, devs, C.byref(params), _ptr(out), C.byref(stats)), "rtb_render_multi")
+    return out, stats.as_dict()
+
+
+def auto_expose(pixels: np.ndarray, spp: float) -> float:
+    lib = capi.load_library()
+    px = np.ascontiguousarray(pixels, dtype=np.float64)
+    e = C.c_double()
+    capi.check(lib, lib.rtb_auto_expose(_ptr(px), px.size // 3, float(spp), C.byref(e)), "rtb_auto_expose")
+    return e.value

@@ -15,10 +15,14 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("RTB200_LIB", PKG_DIR / "librtb200.so"))  # override: debug builds only
 SCENES_LIB_PATH = PKG_DIR / "librtb_scenes.so"
 
-RTB_ABI_VERSION = 1
+RTB_ABI_VERSION = 2
 RTB_FLAG_ISO_PDF_ZERO = 1
 RTB_FLAG_PROPAGATE_NAN = 2
-RTB_TRACE_BRUTE_FORCE = 1
+RTB_FLAG_BVH4, RTB_FLAG_QNODES, RTB_FLAG_BVH_LEAF4, RTB_FLAG_NO_BOX_SCAN, RTB_FLAG_SUN_LIGHT = 0x10, 0x20, 0x40, 0x80, 0x100
+RTB_TRACE_BRUTE_FORCE, RTB_TRACE_WAVEFRONT, RTB_TRACE_SECONDARY = 1, 2, 4
+(OPT_WF_CAPACITY, OPT_EXACT_LEAVES, OPT_SMEM_TOP, OPT_NO_DEFER_RARE, OPT_EXTEND_BLOCKS, OPT_FINISH_BELOW, OPT_PROFILE,
+ OPT_MEGA_BELOW) = range(1, 9)
+ACCUM_SCALE = 4294967296.0
 PIPELINE_DEFAULT, PIPELINE_MEGAKERNEL, PIPELINE_WAVEFRONT = 0, 1, 2
 VARIANT_LIGHTS = 1
 
@@ -53,6 +57,10 @@ class RtbCamera(C.Structure):
                 ("defocus_angle", C.c_double), ("focus_dist", C.c_double), ("background", C.c_double * 3)]
 
 
+class RtbSun(C.Structure):
+    _fields_ = [("direction", C.c_double * 3), ("albedo", C.c_double * 3), ("angular_diameter", C.c_double)]
+
+
 class RtbSceneDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint64),
                 ("objects", C.POINTER(RtbObject)), ("n_objects", C.c_int32),
@@ -62,7 +70,8 @@ class RtbSceneDesc(C.Structure):
                 ("textures", C.POINTER(RtbTexture)), ("n_textures", C.c_int32),
                 ("images", C.POINTER(RtbImage)), ("n_images", C.c_int32),
                 ("perlins", C.POINTER(RtbPerlin)), ("n_perlins", C.c_int32),
-                ("camera", RtbCamera)]
+                ("camera", RtbCamera),
+                ("suns", C.POINTER(RtbSun)), ("n_suns", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RtbRay(C.Structure):
@@ -90,10 +99,13 @@ class RtbRenderParams(C.Structure):
 class RtbStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("node_visits", C.c_uint64),
                 ("prim_tests", C.c_uint64), ("medium_probes", C.c_uint64), ("nonfinite_samples", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("exact_tests", C.c_uint64),
+                ("overflow_rays", C.c_uint64), ("stage_ms", C.c_double * 3)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["stage_ms"] = list(self.stage_ms)
+        return d
 
 
 # numpy views of the ray / hit records (same layout as the C structs: all 8-byte aligned)
@@ -106,7 +118,8 @@ assert RAY_DTYPE.itemsize == C.sizeof(RtbRay) and HIT_DTYPE.itemsize == C.sizeof
 EXPORTS = ["rtb_version", "rtb_device_count", "rtb_last_error", "rtb_scene_create", "rtb_scene_destroy",
            "rtb_scene_info", "rtb_render", "rtb_render_device", "rtb_render_stats", "rtb_trace",
            "rtb_camera_rays", "rtb_medium_interval", "rtb_eval_texture", "rtb_eval_light_pdf",
-           "rtb_write_color"]
+           "rtb_write_color", "rtb_accum_to_pixels", "rtb_render_multi", "rtb_scene_set_option", "rtb_trim_cache",
+           "rtb_auto_expose", "rtb_philox"]
 
 
 class RtbError(RuntimeError):
@@ -143,6 +156,12 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.rtb_eval_texture.argtypes = [vp, i32, vp, i64, vp]
     lib.rtb_eval_light_pdf.argtypes = [vp, vp, i64, vp]
     lib.rtb_write_color.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp]
+    lib.rtb_accum_to_pixels.argtypes = [vp, vp, vp]
+    lib.rtb_render_multi.argtypes = [C.POINTER(RtbSceneDesc), C.c_int, vp, C.POINTER(RtbRenderParams), vp, C.POINTER(RtbStats)]
+    lib.rtb_scene_set_option.argtypes = [vp, C.c_int, i64]
+    lib.rtb_trim_cache.restype = i64
+    lib.rtb_auto_expose.argtypes = [vp, i64, C.c_double, C.POINTER(C.c_double)]
+    lib.rtb_philox.argtypes = [vp, vp, i64, vp]
     if path is None:
         _lib = lib
     return lib

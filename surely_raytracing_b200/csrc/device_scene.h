@@ -57,7 +57,17 @@ enum : int { SPEC_MEDIA = 1,        // constant media present
              SPEC_QUAD_UV = 16,     // a quad whose material reads (u, v)
              SPEC_SPHERE_UV = 32,   // a sphere whose material reads (u, v)
              SPEC_TEXTURES = 64,    // a texture that is not a solid colour (checker / image / noise evaluation)
-             SPEC_ALL = 127 };
+             SPEC_MULTI_LEAF = 128, // BVH leaves of several primitives (RTB_FLAG_BVH_LEAF4): candidates are whole leaves
+             SPEC_ALL = 255 };
+
+// Accumulation buffer: 4 x 64-bit per pixel {r, g, b, count}.  The channel sums are two's-complement fixed point
+// in units of 2^-32 added with integer atomics, so the result does not depend on the order in which paths
+// finish: a render is bit-reproducible, and splitting the stratum range over calls or GPUs changes nothing.
+// Range +-2.1e9 per pixel and channel, resolution 2.3e-10 per sample (an fp32 radiance of 1 carries 6e-8).
+// count = strata accumulated; count >= 2^48 = the pixel received a non-finite sample under RTB_FLAG_PROPAGATE_NAN
+// (a bit low enough that the sum of many devices' buffers cannot carry it out of the word).
+constexpr double ACCUM_SCALE = 4294967296.0;
+constexpr unsigned long long ACCUM_POISON = 1ull << 48;
 
 constexpr int BVH_STACK = 48;     // traversal stack entries (builder rejects deeper trees)
 constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf
@@ -129,6 +139,10 @@ struct alignas(32) DLight {
 };
 static_assert(sizeof(DLight) % 32 == 0, "DLight records must keep prim[] 32-byte aligned (256-bit loads)");
 
+// Sun::new (reference src/object.rs:223-231): unit direction, albedo, limit = 1 - angular_diameter / 180
+struct DSun { float dir[3], albedo[3], limit, pad; };
+constexpr int MAX_SUNS = 4;
+
 struct DCamera {
   double center[3], pixel00[3], du[3], dv[3], disk_u[3], disk_v[3];
   double recip_sqrt_spp;
@@ -166,10 +180,14 @@ struct DScene {
   float scene_mag; // largest |coordinate| of the scene (primitives, media boundaries, camera): scales the f64 rounding bound of the prefilter
   int spec_bits;   // SPEC_* features the scene uses: the wavefront shade kernel picks the smallest instantiation covering them
   DCamera cam;
+  int n_suns;      // > 0 only with RTB_FLAG_SUN_LIGHT (the sun term is commented out at HEAD, src/render.rs:300-308)
+  DSun suns[MAX_SUNS];
 };
 
 struct DStats {
   unsigned long long paths, segments, node_visits, prim_tests, medium_probes, nonfinite;
+  unsigned long long exact_tests;  // f64 reference-order tests run on candidates by the shade stage
+  unsigned long long overflows;    // rays re-traced exactly because their candidates did not fit the slots
 };
 
 }  // namespace rtb

@@ -185,13 +185,12 @@ struct BvhBuilder {
   int max_depth = 0;
   std::vector<std::pair<double, int>> keyed;  // scratch of the exact sweep
   std::vector<double> sweep_area;
-  double kTraversal = 1.0, kIntersect = 3.0;  // SAH costs (RTB_BVH_CI / RTB_BVH_LEAF override, tuning runs)
+  double kTraversal = 1.0, kIntersect = 3.0;  // SAH costs
   int max_leaf = 1;  // measured on c4: one primitive per leaf, Ci/Ct = 3 -> fewest f64 tests (profiles/r01_bvh_sweep.txt)
 
-  explicit BvhBuilder(const std::vector<Baked>& p) : prims(p), order(p.size()) {
+  BvhBuilder(const std::vector<Baked>& p, bool leaves_of_4) : prims(p), order(p.size()) {
     std::iota(order.begin(), order.end(), 0);
-    if (const char* e = getenv("RTB_BVH_CI")) kIntersect = atof(e);
-    if (const char* e = getenv("RTB_BVH_LEAF")) max_leaf = std::max(1, std::min(8, atoi(e)));
+    if (leaves_of_4) { max_leaf = 4; kIntersect = 0.7; }  // RTB_FLAG_BVH_LEAF4: the tuning arm of profiles/r01_bvh_sweep.txt
   }
 
   int build(int first, int count, int depth) {
@@ -376,14 +375,6 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     err = "world must be a list object";
     return RTB_ERR_INVALID;
   }
-  const bool timing = getenv("RTB_TIME_FLATTEN") != nullptr;
-  auto t_start = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!timing) return;
-    auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[rtb flatten] %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
-    t_start = now;
-  };
   out = HostScene();
   out.flags = d.flags;
   out.seed = d.seed;
@@ -440,7 +431,6 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     out.materials.push_back(o);
   }
 
-  lap("tables");
   // ---- object graph ---------------------------------------------------------------------------
   Builder B(d, out, err);
   if (!B.walk(d.world, Xform(), -1, 0)) return err.find("not supported") != std::string::npos ? RTB_ERR_UNSUPPORTED : RTB_ERR_INVALID;
@@ -471,6 +461,21 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     }
     std::memcpy(L.prim, b.payload, sizeof(L.prim));
     out.lights.push_back(L);
+  }
+
+  // ---- suns: accepted and ignored at HEAD (Q23); RTB_FLAG_SUN_LIGHT switches the commented-out term back on
+  if (d.n_suns < 0 || (d.n_suns > 0 && !d.suns)) { err = "bad sun array"; return RTB_ERR_INVALID; }
+  if (d.flags & RTB_FLAG_SUN_LIGHT) {
+    if (d.n_suns > MAX_SUNS) { err = "more suns than the backend holds (4)"; return RTB_ERR_UNSUPPORTED; }
+    for (int k = 0; k < d.n_suns; k++) {  // Sun::new  src/object.rs:223-231
+      const D3 dir = unit({d.suns[k].direction[0], d.suns[k].direction[1], d.suns[k].direction[2]});
+      if (!std::isfinite(dir.x + dir.y + dir.z)) { err = "degenerate sun direction"; return RTB_ERR_INVALID; }
+      DSun& o = out.suns[out.n_suns++];
+      o.dir[0] = (float)dir.x; o.dir[1] = (float)dir.y; o.dir[2] = (float)dir.z;
+      for (int a = 0; a < 3; a++) o.albedo[a] = (float)d.suns[k].albedo[a];
+      o.limit = (float)(1. - d.suns[k].angular_diameter / 180.);
+      o.pad = 0.f;
+    }
   }
 
   // ---- camera: Camera::new  src/render.rs:62-134 ------------------------------------------------
@@ -526,13 +531,11 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     out.scene_mag = round_up(mag);
   }
 
-  lap("walk");
-  BvhBuilder bvh(B.surfaces);
+  BvhBuilder bvh(B.surfaces, (d.flags & RTB_FLAG_BVH_LEAF4) != 0);
   std::vector<int> node_remap;
   if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
   if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
   if (B.surfaces.size() >= (size_t)1 << 26) { err = "more than 2^26 surface primitives (leaf references hold 26 index bits)"; return RTB_ERR_UNSUPPORTED; }
-  lap("bvh build");
   out.bvh_depth = bvh.max_depth;
   out.multi_leaf = 0;
   for (const BuildNode& bn : bvh.nodes) out.multi_leaf |= (bn.left < 0 && bn.count > 1) ? 1 : 0;
@@ -587,11 +590,33 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     const int bits = (b0.kind == PRIM_QUAD ? LEAF_KIND_QUAD : 0) | ((b0.flags & PRIM_FLAG_MOVING) ? LEAF_KIND_MOVING : 0);
     return leaf_make(first, count, bits);
   };
+  // Device indices of the inner nodes: the top TOP_LEVELS levels breadth-first (so that "the first k nodes" are the
+  // top of the tree: what the shared-memory arm of the extend kernel stages), the subtrees below them depth-first
+  // (a ray's consecutive visits stay close in memory).
+  constexpr int TOP_LEVELS = 7;
+  std::vector<int> dev_index(bvh.nodes.size(), -1);
+  {
+    int next = 0;
+    std::vector<std::pair<int, int>> frontier, below;  // (build node, depth)
+    if (!bvh.nodes.empty() && bvh.nodes[0].left >= 0) frontier.push_back({0, 0});
+    for (size_t k = 0; k < frontier.size(); k++) {
+      const int bi = frontier[k].first, depth = frontier[k].second;
+      dev_index[bi] = next++;
+      for (int child : {bvh.nodes[bi].left, bvh.nodes[bi].right})
+        if (bvh.nodes[child].left >= 0) (depth + 1 < TOP_LEVELS ? frontier : below).push_back({child, depth + 1});
+    }
+    std::function<void(int)> dfs = [&](int bi) {
+      dev_index[bi] = next++;
+      for (int child : {bvh.nodes[bi].left, bvh.nodes[bi].right})
+        if (bvh.nodes[child].left >= 0) dfs(child);
+    };
+    for (const auto& b : below) dfs(b.first);
+    out.nodes.resize(4 * (size_t)next);
+  }
   std::function<int(int)> emit_node = [&](int bi) -> int {
     const BuildNode& bn = bvh.nodes[bi];
     if (bn.left < 0) return leaf_ref(bn.first, bn.count);
-    const int self = (int)out.nodes.size() / 4;
-    out.nodes.resize(out.nodes.size() + 4);
+    const int self = dev_index[bi];
     const int refs[2] = {emit_node(bn.left), emit_node(bn.right)};
     const Box* cb[2] = {&bvh.nodes[bn.left].box, &bvh.nodes[bn.right].box};
     float ctr[2][3], half[2][3];
@@ -633,10 +658,10 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   // 1000-radius ground) lose too much to the grid: those keep the 64-byte fp32 nodes.
   // MEASURED on c4 (B200): 35.1 ms extend per step with the 32-byte nodes vs 34.2 ms with the fp32 nodes --
   // the L1 wavefronts fall as intended, but the loop is bound by instruction issue and the 12 extra PRMT
-  // per visit cost more than the loads save.  Kept as an opt-in arm (RTB_QNODES=1) for scenes whose
+  // per visit cost more than the loads save.  Kept as an opt-in arm (RTB_FLAG_QNODES) for scenes whose
   // trees do not fit L1; the surface-area test still vetoes it where the grid is too coarse.
   out.use_qnodes = 0;
-  if (const char* e = getenv("RTB_QNODES")) out.use_qnodes = (atoi(e) != 0 && !B.surfaces.empty() && sa_quant <= 1.03 * sa_exact) ? 1 : 0;
+  if (d.flags & RTB_FLAG_QNODES) out.use_qnodes = (!B.surfaces.empty() && sa_quant <= 1.03 * sa_exact) ? 1 : 0;
   // ---- BVH4: collapse every other level of the emitted BVH2 (same fp32 boxes, so the cull is the same) ----
   // A 4-wide node halves the dependent node steps per ray (c4: 12.6 -> 6.9 visits).
 #if !defined(RTB_SLAB_CENTER)
@@ -685,13 +710,12 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     emit4(0);
     // MEASURED on c4 (B200, ncu in profiles/): visits per ray fall 12.3 -> 6.9, but a 128-byte node is seven
     // load instructions per visit and the L1 data pipe -- already at 75 % with the BVH2 -- saturates
-    // (81 %, long-scoreboard stalls 4.5 -> 6.1 per issue): 555 vs 487 us per launch.  Opt-in (RTB_BVH4=1).
+    // (81 %, long-scoreboard stalls 4.5 -> 6.1 per issue): 555 vs 487 us per launch.  Opt-in (RTB_FLAG_BVH4).
     out.use_bvh4 = 0;
-    if (const char* e = getenv("RTB_BVH4")) out.use_bvh4 = atoi(e) != 0 ? 1 : 0;
+    if (d.flags & RTB_FLAG_BVH4) out.use_bvh4 = 1;
   }
 #endif
   if (out.nodes4.empty()) out.nodes4.assign(8, float4{0.f, 0.f, 0.f, 0.f});
-  lap("emit");
   // ---- media: boundary primitives after the surfaces, in DFS order ----------------------------------
   for (size_t mi = 0; mi < B.boundaries.size(); mi++) {
     DMedium m{};
@@ -706,7 +730,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     {
       bool all_quads = m.n_prims > 0;
       for (const Baked& b : B.boundaries[mi]) all_quads = all_quads && b.kind == PRIM_QUAD;
-      if (all_quads && !getenv("RTB_NO_BOX_SCAN")) m.cls_fast |= 0x200;
+      if (all_quads && !(d.flags & RTB_FLAG_NO_BOX_SCAN)) m.cls_fast |= 0x200;
     }
     for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
     {
@@ -723,6 +747,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     if (!(m.cls_fast & 0x100)) out.spec_bits |= SPEC_GENERIC_MEDIA;
   }
   if (!out.lights.empty()) out.spec_bits |= SPEC_LIGHTS;
+  if (out.multi_leaf) out.spec_bits |= SPEC_MULTI_LEAF;
   for (const DTexture& t : out.textures)
     if (t.kind != TEX_SOLID) out.spec_bits |= SPEC_TEXTURES;
   // deferred shading of the textured classes (wavefront.cu, k_wf_shade_rare) needs every non-solid texture to hang

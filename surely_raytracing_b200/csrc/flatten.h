@@ -38,6 +38,8 @@ struct HostScene {
   std::vector<uint8_t> perlin_perm;
   std::vector<DLight> lights;
   DCamera cam;
+  int n_suns = 0;
+  DSun suns[MAX_SUNS] = {};
   int n_surface_prims = 0;
   int bvh_depth = 0;
   uint32_t flags = 0;

@@ -27,6 +27,7 @@ __device__ __forceinline__ bool tile_pixel(const DCamera& cam, long long warp_gl
 
 __device__ __forceinline__ void flush_stats(const DStats& local, DStats* global) {
   atomicAdd(&global->paths, local.paths);
+  atomicAdd(&global->exact_tests, local.prim_tests);  // every test of this kernel is an exact one
   atomicAdd(&global->segments, local.segments);
   atomicAdd(&global->node_visits, local.node_visits);
   atomicAdd(&global->prim_tests, local.prim_tests);
@@ -38,18 +39,18 @@ __device__ __forceinline__ void flush_stats(const DStats& local, DStats* global)
 // megakernel: the loop of render_par_lights (reference src/render.rs:179-191) with one thread per
 // pixel.  A lane whose path ends immediately starts its next stratum, so every lane of the warp
 // keeps tracing segments until its pixel's sample range is exhausted (per-lane regeneration).
-// The pixel's sum is kept in f64 registers and added to the fp32 accumulation buffer once, by the
-// one thread that owns the pixel: no atomics, bit-reproducible.
+// The pixel's sum is kept in registers as the same 64-bit fixed point the accumulation buffer holds and added
+// once, by the one thread that owns the pixel: no atomics, and the same bits as any other split of the samples.
 // ------------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene S, long long s_begin,
-                                                     long long s_end, float4* __restrict__ accum,
+                                                     long long s_end, unsigned long long* __restrict__ accum,
                                                      DStats* __restrict__ stats) {
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t pixel;
   if (!tile_pixel(S.cam, warp_global, threadIdx.x & 31, pixel)) return;
-  DStats st = {0, 0, 0, 0, 0, 0};
-  double sum_r = 0., sum_g = 0., sum_b = 0.;
+  DStats st = {};
+  unsigned long long sum_r = 0, sum_g = 0, sum_b = 0, poison = 0;
   long long s = s_begin;
   PathState ps;
   bool alive = false;
@@ -69,20 +70,22 @@ __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DSc
     alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);
     if (!alive) {
       const bool finite = (fabsf(Lr) < 3.0e38f) && (fabsf(Lg) < 3.0e38f) && (fabsf(Lb) < 3.0e38f);
-      if (finite || (S.flags & 2u)) {
-        sum_r += (double)Lr; sum_g += (double)Lg; sum_b += (double)Lb;
+      if (finite) {
+        sum_r += accum_fixed(Lr); sum_g += accum_fixed(Lg); sum_b += accum_fixed(Lb);
+      } else if (S.flags & 2u) {
+        poison = ACCUM_POISON;
       } else if (STATS) {
         st.nonfinite++;
       }
     }
   }
-  float4 a = accum[pixel];
-  a.x += (float)sum_r; a.y += (float)sum_g; a.z += (float)sum_b; a.w += (float)(s_end - s_begin);
-  accum[pixel] = a;
+  unsigned long long* a = accum + 4ull * pixel;
+  a[0] += sum_r; a[1] += sum_g; a[2] += sum_b;
+  a[3] = (a[3] + (unsigned long long)(s_end - s_begin)) | poison;
   if (STATS) flush_stats(st, stats);
 }
 
-cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, float4* d_accum, DStats* d_stats,
+cudaError_t launch_render_mega(const DScene& S, int64_t s_begin, int64_t s_end, unsigned long long* d_accum, DStats* d_stats,
                                bool collect_stats, cudaStream_t stream, int* launches) {
   const long long tiles = (long long)((S.cam.width + 7) / 8) * ((S.cam.height + 3) / 4);
   const int block = 128;
@@ -225,15 +228,34 @@ cudaError_t launch_write_color(const double* d_pixels, int64_t n_values, double 
   return cudaGetLastError();
 }
 
-__global__ void k_accum_to_f64(const float4* __restrict__ accum, long long n, double* __restrict__ rgb) {
+__global__ void k_accum_to_f64(const unsigned long long* __restrict__ accum, long long n, double* __restrict__ rgb, int add) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 a = accum[i];
-  rgb[3 * i] = (double)a.x; rgb[3 * i + 1] = (double)a.y; rgb[3 * i + 2] = (double)a.z;
+  const bool poisoned = accum[4 * i + 3] >= ACCUM_POISON;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double v = (double)(long long)accum[4 * i + c] * (1.0 / ACCUM_SCALE);
+    if (poisoned) v = RTB_INF - RTB_INF;
+    rgb[3 * i + c] = add ? rgb[3 * i + c] + v : v;
+  }
 }
-cudaError_t launch_accum_to_f64(const float4* d_accum, int64_t n_pixels, double* d_pixels_rgb, cudaStream_t stream) {
+cudaError_t launch_accum_to_f64(const unsigned long long* d_accum, int64_t n_pixels, double* d_pixels_rgb, int add, cudaStream_t stream) {
   if (n_pixels <= 0) return cudaSuccess;
-  k_accum_to_f64<<<(unsigned)((n_pixels + 255) / 256), 256, 0, stream>>>(d_accum, n_pixels, d_pixels_rgb);
+  k_accum_to_f64<<<(unsigned)((n_pixels + 255) / 256), 256, 0, stream>>>(d_accum, n_pixels, d_pixels_rgb, add);
+  return cudaGetLastError();
+}
+
+// Random123 known-answer hook: the device's own philox4x32_10 (rtb_device.cuh) on caller-given counters / keys
+__global__ void k_philox(const uint32_t* __restrict__ ctr_key, long long n, uint32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o[4];
+  philox4x32_10(ctr_key[6 * i], ctr_key[6 * i + 1], ctr_key[6 * i + 2], ctr_key[6 * i + 3], ctr_key[6 * i + 4], ctr_key[6 * i + 5], o);
+  out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+}
+cudaError_t launch_philox(const uint32_t* d_ctr_key, int64_t n, uint32_t* d_out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_philox<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_ctr_key, n, d_out);
   return cudaGetLastError();
 }
 

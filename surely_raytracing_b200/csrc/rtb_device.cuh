@@ -838,14 +838,21 @@ RTB_DEV bool medium_precheck(const DMedium& m, double ox, double oy, double oz, 
 }
 
 template <bool BOXSCAN = true, bool GENERIC = true>
-RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, double ox, double oy, double oz, float dx, float dy, float dz,
-                                 double time, double tmin, double tmax, float U) {
-  if (!medium_precheck(m, ox, oy, oz, dx, dy, dz, tmin, tmax, U)) return RTB_INF;
-  Ray r;
-  r.ox = ox; r.oy = oy; r.oz = oz;
-  r.dx = (double)dx; r.dy = (double)dy; r.dz = (double)dz;
-  r.time = time;
+RTB_DEV double medium_event_lazy(const DScene& S, const DMedium& m, const Ray& r, double tmin, double tmax, float U) {
+  // (a primary ray's f64 direction is rounded for the precheck only: 6e-8 relative against margins of 1e-3 and 2e-6)
+  if (!medium_precheck(m, r.ox, r.oy, r.oz, (float)r.dx, (float)r.dy, (float)r.dz, tmin, tmax, U)) return RTB_INF;
   return medium_event<BOXSCAN, GENERIC>(S, m, r, tmin, tmax, U);
+}
+
+// one sample's radiance as the fixed-point addend of the accumulation buffer (device_scene.h ACCUM_SCALE);
+// the conversion saturates, a finite sample can at worst pin its pixel
+RTB_DEV unsigned long long accum_fixed(float L) {
+#if defined(__CUDACC__)
+  return (unsigned long long)__double2ll_rn((double)L * ACCUM_SCALE);
+#else
+  const double v = (double)L * ACCUM_SCALE;
+  return (unsigned long long)(long long)(v >= 9.2e18 ? 9.2e18 : (v <= -9.2e18 ? -9.2e18 : nearbyint(v)));
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1130,7 +1137,15 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
                    DStats* st, bool stats) {
   const Ray& r = ps.ray;
   if (!(ev.t < RTB_INF)) {  // miss: cam.background  src/render.rs:298-309
-    Lr += ps.bx * S.cam.background[0]; Lg += ps.by * S.cam.background[1]; Lb += ps.bz * S.cam.background[2];
+    float er = S.cam.background[0], eg = S.cam.background[1], eb = S.cam.background[2];
+    if (S.n_suns > 0) {  // `cam.background + sun_light` (the term HEAD comments out; RTB_FLAG_SUN_LIGHT): Sun::_hit  object.rs:232-239
+      const V3 ud = normalize(v3((float)r.dx, (float)r.dy, (float)r.dz));
+      for (int k = 0; k < S.n_suns; k++)
+        if (dot(ud, v3(S.suns[k].dir[0], S.suns[k].dir[1], S.suns[k].dir[2])) > S.suns[k].limit) {
+          er += S.suns[k].albedo[0]; eg += S.suns[k].albedo[1]; eb += S.suns[k].albedo[2];
+        }
+    }
+    Lr += ps.bx * er; Lg += ps.by * eg; Lb += ps.bz * eb;
     return false;
   }
   const double px = dadd(r.ox, dmul(ev.t, r.dx)), py = dadd(r.oy, dmul(ev.t, r.dy)), pz = dadd(r.oz, dmul(ev.t, r.dz));  // Ray::at

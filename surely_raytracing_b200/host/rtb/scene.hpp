@@ -46,6 +46,13 @@ inline Vec3 operator*(const Vec3& a, const Vec3& b) { return Vec3(a.x_ * b.x_, a
 inline Vec3 operator*(double t, const Vec3& a) { return Vec3(t * a.x_, t * a.y_, t * a.z_); }
 inline Vec3 operator*(const Vec3& a, double t) { return t * a; }
 inline Vec3 operator/(const Vec3& a, double t) { return Vec3(a.x_ / t, a.y_ / t, a.z_ / t); }  // true division, vec3.rs:145-151
+inline Vec3& operator+=(Vec3& a, const Vec3& b) { a = a + b; return a; }   // vec3.rs:74-80 (AddAssign)
+inline Vec3& operator*=(Vec3& a, double t) { a = a * t; return a; }        // vec3.rs:121-127 (MulAssign<f64>)
+inline Vec3& operator/=(Vec3& a, double t) { a = a / t; return a; }        // vec3.rs:153-157
+inline double dot(const Vec3& a, const Vec3& b) { return a.x_ * b.x_ + a.y_ * b.y_ + a.z_ * b.z_; }                 // vec3.rs:167
+inline Vec3 cross(const Vec3& a, const Vec3& b) {                                                                    // vec3.rs:171
+  return Vec3(a.y_ * b.z_ - a.z_ * b.y_, a.z_ * b.x_ - a.x_ * b.z_, a.x_ * b.y_ - a.y_ * b.x_);
+}
 inline Vec3 unit_vector(const Vec3& v) { return v / v.length(); }
 
 // ---- utils.rs: host-side construction randomness ----------------------------------------------
@@ -300,11 +307,13 @@ struct ConstantMedium {
   }
 };
 
-// object.rs:216-241 -- accepted and ignored by the integrator (Q23); kept for signature parity.
+// object.rs:216-241 -- accepted and ignored by the integrator at HEAD (the sun term of ray_color is commented
+// out, render.rs:300-308; Q23).  The records still travel to the library, which adds the term back under
+// RTB_FLAG_SUN_LIGHT.
 struct Sun {
-  Vec3 direction; Color albedo; double limit;
+  Vec3 direction; Color albedo; double limit; double angular_diameter;
   static Sun new_(Vec3 direction, Color albedo, double angular_diameter) {
-    return Sun{unit_vector(direction), albedo, 1. - angular_diameter / 180.};
+    return Sun{unit_vector(direction), albedo, 1. - angular_diameter / 180., angular_diameter};
   }
 };
 
@@ -350,6 +359,7 @@ class FlatScene {
   std::vector<RtbImage> images;
   std::vector<RtbPerlin> perlins;
   std::vector<std::shared_ptr<const std::vector<uint8_t>>> image_bytes;  // keeps RtbImage.rgb alive
+  std::vector<RtbSun> suns;
   int32_t world = -1;
   RtbCamera camera{};
   uint32_t flags = 0;
@@ -360,6 +370,27 @@ class FlatScene {
     world = emit_list(world_list.objects, RTB_OBJ_LIST);
     if (light_list)
       for (const Object& o : light_list->objects) lights.push_back(emit(o));
+  }
+  // `lights: Arc<Object>` (render.rs:149): pdf_value / random dispatch on ANY object (object.rs:53-69) -- a list
+  // contributes its members, a bare Quad or Sphere is a one-element list, anything else the Hittable defaults
+  struct LightObject { Object object; };
+  FlatScene(const Camera& cam, const HittableList& world_list, const LightObject& l) {
+    camera = cam.to_abi();
+    world = emit_list(world_list.objects, RTB_OBJ_LIST);
+    if (l.object) {
+      if (l.object->kind == RTB_OBJ_LIST) for (const Object& o : l.object->children) lights.push_back(emit(o));
+      else lights.push_back(emit(l.object));
+    }
+  }
+  void set_suns(const std::vector<Sun>& in) {
+    suns.clear();
+    for (const Sun& s : in) {
+      RtbSun r{};
+      r.direction[0] = s.direction.x(); r.direction[1] = s.direction.y(); r.direction[2] = s.direction.z();
+      r.albedo[0] = s.albedo.x(); r.albedo[1] = s.albedo.y(); r.albedo[2] = s.albedo.z();
+      r.angular_diameter = s.angular_diameter;
+      suns.push_back(r);
+    }
   }
 
   RtbSceneDesc desc() const {
@@ -374,6 +405,7 @@ class FlatScene {
     d.images = images.data(); d.n_images = (int32_t)images.size();
     d.perlins = perlins.data(); d.n_perlins = (int32_t)perlins.size();
     d.camera = camera;
+    d.suns = suns.data(); d.n_suns = (int32_t)suns.size();
     return d;
   }
 

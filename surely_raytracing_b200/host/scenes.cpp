@@ -212,6 +212,21 @@ FlatScene* scene_three_spheres(int width, int spp, int depth) {  // main.rs:92-1
                             Point3(0., 0., -1.), Vec3(0., 1., 0.), 2., 1., Color(0.7, 0.8, 1.));
   return new FlatScene(cam, world.create_bvh(), nullptr);
 }
+FlatScene* scene_sun_spheres(int width, int spp, int depth) {  // main.rs:32-90 (scene -2: suns + auto_exposure)
+  HittableList world;
+  Material left = Dielectric::new_(1.5, Color(1., 1., 1.));
+  world.add(Sphere::new_(Point3(0., 0., -1.), 0.5, Lambertian::new_(Color(0.1, 0.2, 0.5))));
+  world.add(Sphere::new_(Point3(-1., 0., -1.25), 0.5, left));
+  world.add(Sphere::new_(Point3(-1., 0., -1.25), -0.4, left));
+  world.add(Sphere::new_(Point3(0., -100.5, -1.), 100., Lambertian::new_(Color(0.8, 0.8, 0.0))));
+  world.add(Sphere::new_(Point3(1., 0., -0.75), 0.5, Metal::new_(Color(0.8, 0.6, 0.2), 0.)));
+  Camera cam = Camera::new_(16. / 9., pick(width, 640), pick(spp, 1000), pick(depth, 50), 90., Point3(0., 0., 0.),
+                            Point3(0., 0., -1.), Vec3(0., 1., 0.), 0., 1., Color(0.02, 0.05, 0.1));
+  cam.auto_exposure = true;
+  FlatScene* f = new FlatScene(cam, world, nullptr);
+  f->set_suns({Sun::new_(Vec3(-1., 1., 1.), Color(1., 1., 1.) * 10., 2.)});
+  return f;
+}
 FlatScene* two_spheres(int width, int spp, int depth) {  // main.rs:212-250
   HittableList world;
   Texture checker = CheckerTexture::from_color(0.3, Color(0.2, 0.3, 0.1), Color(0.9, 0.9, 0.9));
@@ -293,6 +308,7 @@ void* rtbs_build(const char* name, int width, int spp, int depth, uint64_t seed,
     else if (n == "c4" || n == "final_scene") f = final_scene(width, spp, depth, variant, seed);
     else if (n == "c5" || n == "cornell_box") f = cornell_box(width, spp, depth, true);
     else if (n == "scene_three_spheres") f = scene_three_spheres(width, spp, depth);
+    else if (n == "scene_sun_spheres") f = scene_sun_spheres(width, spp, depth);
     else if (n == "two_spheres") f = two_spheres(width, spp, depth);
     else if (n == "earth") f = earth(width, spp, depth, seed);
     else if (n == "two_perlin_spheres") f = two_perlin_spheres(width, spp, depth);

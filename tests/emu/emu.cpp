@@ -69,7 +69,7 @@ int emu_scene_info(void* p, RtbSceneInfo* info) {
 int emu_render(void* p, long long s_begin, long long s_end, double* rgb, unsigned long long* stats6) {
   const Emu* e = static_cast<Emu*>(p);
   const DScene& S = e->dev;
-  DStats st = {0, 0, 0, 0, 0, 0};
+  DStats st = {};
   const int n = S.cam.width * S.cam.height;
   for (int pixel = 0; pixel < n; pixel++) {
     double sr = 0, sg = 0, sb = 0;
@@ -198,7 +198,7 @@ extern "C" long long emu_slow_rays(void* p, long long s_begin, long long s_end, 
       float Lr = 0, Lg = 0, Lb = 0;
       bool alive = true;
       while (alive) {
-        DStats st = {0, 0, 0, 0, 0, 0};
+        DStats st = {};
         Event ev;
         const Ray r = ps.ray;
         extend<true>(S, ps, ev, &st);
@@ -215,7 +215,7 @@ extern "C" long long emu_slow_rays(void* p, long long s_begin, long long s_end, 
           }
           found++;
         }
-        DStats dummy = {0, 0, 0, 0, 0, 0};
+        DStats dummy = {};
         alive = shade(S, ps, ev, Lr, Lg, Lb, &dummy, false);
       }
     }
@@ -229,6 +229,11 @@ extern "C" int emu_defer_ok(void* p) { return static_cast<Emu*>(p)->host.defer_o
 extern "C" int emu_leaf_roundtrip(int first, int count, int kind_bits) {
   const int ref = leaf_make(first, count, kind_bits);
   return ref < 0 && leaf_first(ref) == first && leaf_count(ref) == count && leaf_kind_bits(ref) == kind_bits;
+}
+// child references of inner node `node` of the BVH2 (device numbering)
+extern "C" void emu_node_children(void* p, int node, int* out2) {
+  const HostScene& h = static_cast<Emu*>(p)->host;
+  std::memcpy(out2, &h.nodes[4 * (size_t)node + 3], 8);
 }
 // every leaf of the BVH2 carries the kind bits of its (single) primitive; returns the number of violations
 extern "C" int emu_check_leaf_refs(void* p) {
@@ -303,7 +308,7 @@ extern "C" int emu_check_qnodes(void* p, const QRay* rays, long long n, long lon
     }
     Hit hf;
     hit_reset(hf);
-    DStats st = {0, 0, 0, 0, 0, 0};
+    DStats st = {};
     closest_surface<true>(S, r, 0.0001, hf, &st);
     visits_f += (double)st.node_visits;
     if (hf.prim != hq.prim || hf.t != hq.t) mism_f++;
@@ -366,7 +371,7 @@ extern "C" int emu_check_nodes4(void* p, const QRay* rays, long long n, long lon
     }
     Hit h2;
     hit_reset(h2);
-    DStats st = {0, 0, 0, 0, 0, 0};
+    DStats st = {};
     closest_surface<true>(S, r, 0.0001, h2, &st);
     visits2 += (double)st.node_visits;
     if (h2.prim != h4.prim || h2.t != h4.t) mism2++;

@@ -33,7 +33,20 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.RtbPerlin) == 256 * 24 + 3 * 256 * 4
     assert C.sizeof(capi.RtbCamera) == 8 + 16 + 8 + 72 + 16 + 24
     assert C.sizeof(capi.RtbRay) == 64 and C.sizeof(capi.RtbHit) == 16 + 8 + 48 + 16
-    assert C.sizeof(capi.RtbRenderParams) == 24 and C.sizeof(capi.RtbStats) == 64
+    assert C.sizeof(capi.RtbRenderParams) == 24 and C.sizeof(capi.RtbStats) == 64 + 16 + 24
+    assert C.sizeof(capi.RtbSun) == 56
+    # RtbSceneDesc: 16 header + 5 x (pointer, count|index pairs) ... checked against the compiler below
+    import subprocess, tempfile, textwrap
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include "rtb200.h"
+        int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(RtbSceneDesc), sizeof(RtbStats), sizeof(RtbSceneInfo), sizeof(RtbCamera)); return 0; }
+    """)
+    with tempfile.TemporaryDirectory() as td:
+        (Path(td) / "s.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", f"{td}/s", f"{td}/s.c"], check=True)   # the header is plain C
+        sizes = list(map(int, subprocess.run([f"{td}/s"], capture_output=True, text=True, check=True).stdout.split()))
+    assert sizes == [C.sizeof(capi.RtbSceneDesc), C.sizeof(capi.RtbStats), C.sizeof(capi.RtbSceneInfo), C.sizeof(capi.RtbCamera)]
 
 
 def _create(desc):

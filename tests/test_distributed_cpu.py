@@ -71,7 +71,9 @@ def _worker(rank, world, port, out_path):
     o = orc.OracleScene(BuiltScene("c2", width=40, spp=25))
     lo, hi = split_samples(o.info.spp_used, world, rank)
     s, _ = o.render(lo, hi, sampler=orc.SAMPLER_KEYED, threads=1)
-    accum = torch.from_numpy(s.astype(np.float32))      # fp32 accumulation buffers, like the GPU path
+    from surely_raytracing_b200.distributed import to_fixed
+    accum = torch.from_numpy(to_fixed(s))               # int64 fixed-point accumulation buffers, like the GPU path
+    np.save(out_path + f".part{rank}.npy", accum.numpy())
     reduce_to_root(accum, 0)
     if rank == 0:
         np.save(out_path, accum.numpy())
@@ -89,6 +91,23 @@ def test_two_rank_split_and_reduce_equals_single_rank(tmp_path):
     out = tmp_path / "reduced.npy"
     mp.spawn(_worker, args=(2, port, str(out)), nprocs=2, join=True)
     got = np.load(out)
+    assert got.dtype == np.int64
+    parts = [np.load(str(out) + f".part{r}.npy") for r in range(2)]
+    assert np.array_equal(got, parts[0] + parts[1])       # integer sums: the reduce is exact, whatever the split
     o = orc.OracleScene(BuiltScene("c2", width=40, spp=25))
     full, _ = o.render(sampler=orc.SAMPLER_KEYED, threads=1)
-    assert np.allclose(got, full, rtol=1e-6, atol=1e-5)
+    assert np.allclose(got / 4294967296.0, full, rtol=1e-12, atol=2 ** -31)
+
+
+def test_strong_scaling_slices_tile_each_pass():
+    """bench.py --scaling strong: the ranks' slices of a pass are contiguous, disjoint and cover the pass's rows."""
+    from surely_raytracing_b200.distributed import strong_pass
+    for world in (1, 2, 3, 8):
+        for rows in (1, 10):
+            for k in range(12):
+                lo, hi = pass_rows(k, 1, 0, 100, rows)
+                cuts = [strong_pass(k, world, r, 100, rows) for r in range(world)]
+                assert cuts[0][0] == lo and cuts[-1][1] == hi
+                assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+                sizes = [b - a for a, b in cuts]
+                assert max(sizes) - min(sizes) <= 1

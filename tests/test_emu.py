@@ -226,19 +226,38 @@ def test_leaf_reference_codec():
                 assert lib.emu_leaf_roundtrip(first, count, kind) == 1
 
 
-def test_multi_primitive_leaves_on_the_host_build(monkeypatch):
-    """RTB_BVH_LEAF > 1: leaves of several primitives go through the generic leaf loop (prim_info read per test)."""
-    monkeypatch.setenv("RTB_BVH_LEAF", "4")
-    monkeypatch.setenv("RTB_BVH_CI", "0.7")
-    b = BuiltScene("c4", width=96, spp=4)
+def test_multi_primitive_leaves_on_the_host_build():
+    """RTB_FLAG_BVH_LEAF4: leaves of several primitives go through the generic leaf loop (prim_info read per test),
+    and the candidate scheme then carries whole leaves as candidates."""
+    b = BuiltScene("c4", width=96, spp=4, flags=capi.RTB_FLAG_BVH_LEAF4)
     e = EmuScene(b)
     assert e.leaf_ref_violations() == 0
+    assert e.spec_bits() & 128                                             # SPEC_MULTI_LEAF
     rays = orc.OracleScene(b, use_bvh=False).camera_rays()
     he, hb = e.trace(rays), e.trace(rays, capi.RTB_TRACE_BRUTE_FORCE)
     assert (hb["prim"] == he["prim"]).all() and np.array_equal(hb["t"], he["t"])
-    monkeypatch.delenv("RTB_BVH_LEAF")
-    monkeypatch.delenv("RTB_BVH_CI")
-    e1 = EmuScene(b)
+    hc, st = e.trace_candidates(rays)
+    assert (hc["prim"] == he["prim"]).all() and np.array_equal(hc["t"], he["t"]) and st["overflows"] < 0.01 * len(rays)
+    b1 = BuiltScene("c4", width=96, spp=4)
+    e1 = EmuScene(b1)
     assert e.info.n_bvh_nodes < 0.7 * e1.info.n_bvh_nodes
     h1 = e1.trace(rays)
     assert (h1["prim"] == he["prim"]).all() and np.array_equal(h1["t"], he["t"])
+
+
+def test_top_levels_of_the_tree_come_first_in_memory():
+    """The flattener numbers the top 7 levels of the BVH breadth-first (what the shared-memory arm of the extend
+    kernel stages) and the subtrees below them depth-first: children of the first nodes are themselves early."""
+    import ctypes as C
+    from tests.emu.emu_lib import load
+    lib = load()
+    e = EmuScene(BuiltScene("c4", width=32, spp=4))
+    lib.emu_node_children.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    kids = np.zeros(2, dtype=np.int32)
+    top, frontier = [], [(0, 0)]
+    while frontier:
+        node, d = frontier.pop(0)
+        top.append(node)
+        lib.emu_node_children(e._h, node, kids.ctypes.data_as(C.c_void_p))
+        frontier += [(int(k), d + 1) for k in kids if k >= 0 and d + 1 < 7]
+    assert 32 < len(top) <= 127 and top == list(range(len(top)))          # breadth-first, a prefix of the array

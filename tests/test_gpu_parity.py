@@ -40,6 +40,101 @@ def test_first_hit_parity_full_resolution(cfg):
     assert (sb["prim"] == sg["prim"]).all()
 
 
+def _same_hits(a, b):
+    same_t = (a["t"] == b["t"]) | (np.isinf(a["t"]) & np.isinf(b["t"]))
+    return bool((a["prim"] == b["prim"]).all() and same_t.all() and np.array_equal(a["p"], b["p"]) and
+                np.array_equal(a["normal"], b["normal"]) and (a["front_face"] == b["front_face"]).all())
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5"])
+def test_first_hit_parity_through_the_kernels_rtb_render_runs(cfg):
+    """RTB_TRACE_WAVEFRONT: the rays travel as queue records through k_wf_extend (conservative fp32 classification,
+    <= 2 candidates), k_wf_extend_exact (overflows) and the exact resolution of the shade stage -- the SHIPPED traversal,
+    not the harness kernel.  Pixel-centre rays at the config's full resolution travel as PRIMARY records (f64
+    directions, what get_ray produces): ids bit-exact against the oracle, t / normal / uv to 1e-9.  Seeded secondary rays
+    travel as SECONDARY records (directions rounded to fp32, as every scattered ray of the pipeline is) and are held to
+    the oracle on the same rounded directions.  The round-1 arm (f64 tests inside the traversal, RTB_OPT_EXACT_LEAVES)
+    must give the very same records, and so must the harness kernel."""
+    b = BuiltScene(cfg, spp=4)
+    o = orc.OracleScene(b, use_bvh=False if cfg != "c4" else True)
+    g = Scene(b)
+    rays = g.camera_rays()
+    full = rays
+    if cfg == "c4":
+        rays = rays[:: 4]
+    ho = o.trace(rays)
+    hw = g.trace(rays, capi.RTB_TRACE_WAVEFRONT)
+    st = g.render_stats()
+    mism, t_rel, dn, duv = util.hit_errors(ho, hw)
+    assert mism == 0, f"{mism} first-hit id mismatches through k_wf_extend"
+    assert t_rel < 1e-9 and dn < 1e-9 and duv < 1e-9, (t_rel, dn, duv)
+    assert (ho["front_face"] == hw["front_face"]).all() and (ho["material"] == hw["material"]).all()
+    assert st["overflow_rays"] < 0.005 * len(rays) and st["exact_tests"] < 1.05 * len(rays), st
+    # all pixel centres: pipeline kernels == harness kernel == exact-leaves arm, record for record
+    hh = g.trace(full)
+    hw_full = g.trace(full, capi.RTB_TRACE_WAVEFRONT)
+    assert _same_hits(hh, hw_full)
+    g.set_option(capi.OPT_EXACT_LEAVES, 1)
+    assert _same_hits(hh, g.trace(full, capi.RTB_TRACE_WAVEFRONT))
+    g.set_option(capi.OPT_EXACT_LEAVES, 0)
+    g.set_option(capi.OPT_SMEM_TOP, 1)
+    assert _same_hits(hh, g.trace(full, capi.RTB_TRACE_WAVEFRONT))
+    g.set_option(capi.OPT_SMEM_TOP, 0)
+    # what carrying bounce-0 directions in fp32 (round 1) would have cost: ids that differ from the f64 reference rays
+    r32 = full.copy()
+    r32["direction"] = r32["direction"].astype(np.float32)
+    h32 = g.trace(r32, capi.RTB_TRACE_WAVEFRONT | capi.RTB_TRACE_SECONDARY)
+    print(f"{cfg}: pixel-centre ids that change when the direction is rounded to fp32: {int((h32['prim'] != hh['prim']).sum())} of {len(full)}")
+    # secondary records: fp32-rounded directions and time, against the oracle on the same rays
+    o.set_use_bvh(False)
+    sec = util.secondary_rays(ho, np.random.default_rng(11), n_max=20000 if cfg != "c4" else 4000)
+    sec["direction"] = sec["direction"].astype(np.float32)
+    sec["time"] = sec["time"].astype(np.float32)
+    so, sw = o.trace(sec), g.trace(sec, capi.RTB_TRACE_WAVEFRONT | capi.RTB_TRACE_SECONDARY)
+    mism, t_rel, dn, duv = util.hit_errors(so, sw)
+    assert mism == 0 and t_rel < 1e-7 and dn < 1e-7 and duv < 1e-7, (mism, t_rel, dn, duv)
+    assert _same_hits(g.trace(sec), sw)
+    with pytest.raises(capi.RtbError):
+        bad = sec[:4].copy()
+        bad["t_min"] = 1e-3
+        g.trace(bad, capi.RTB_TRACE_WAVEFRONT)
+
+
+def test_candidate_traversal_equals_brute_force_on_random_rays():
+    """2M random rays through c4 (axis-parallel ones included) as queue records: the candidate traversal finds the
+    brute-force closest hit, prim and t bit for bit."""
+    b = BuiltScene("c4", width=64, spp=4)
+    g = Scene(b)
+    rng = np.random.default_rng(5)
+    n = 2_000_000
+    rays = np.zeros(n, dtype=capi.RAY_DTYPE)
+    rays["origin"] = rng.uniform([-1200, -50, -1200], [1200, 700, 1200], (n, 3))
+    d = rng.normal(size=(n, 3))
+    d[: n // 10, rng.integers(0, 3)] = 0.0
+    rays["direction"] = d.astype(np.float32)
+    rays["time"] = rng.uniform(0, 1, n).astype(np.float32)
+    rays["t_min"] = 1e-4
+    hb = g.trace(rays, capi.RTB_TRACE_BRUTE_FORCE)
+    for flags in (capi.RTB_TRACE_WAVEFRONT, capi.RTB_TRACE_WAVEFRONT | capi.RTB_TRACE_SECONDARY):
+        hw = g.trace(rays, flags)
+        assert (hb["prim"] == hw["prim"]).all() and np.array_equal(hb["t"], hw["t"])
+    assert g.render_stats()["overflow_rays"] < 0.002 * n
+
+
+def test_device_philox_known_answers():
+    """Random123's Philox4x32-10 known-answer vectors on the DEVICE copy of the generator (rtb_device.cuh), and the
+    device against the oracle's copy on random counters."""
+    g = Scene(BuiltScene("c2", width=16, spp=4))
+    kat = np.array([[0, 0, 0, 0, 0, 0], [0xFFFFFFFF] * 6,
+                    [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0]], dtype=np.uint32)
+    want = np.array([[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8], [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+                     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]], dtype=np.uint32)
+    assert np.array_equal(g.philox(kat), want)
+    rng = np.random.default_rng(1)
+    ck = rng.integers(0, 2 ** 32, (5000, 6), dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(g.philox(ck), np.array([orc.philox(c[:4], c[4:]) for c in ck], dtype=np.uint32))
+
+
 def test_bvh_cull_is_conservative_on_random_rays():
     """2M random rays through c4: BVH traversal == brute force (ids and t bit-identical)."""
     b = BuiltScene("c4", width=64, spp=4)
@@ -137,74 +232,112 @@ def test_image_statistics_against_the_committed_oracle_render(name, pipeline):
 
 
 @pytest.mark.parametrize("pipeline", PIPELINES)
-def test_deterministic_and_additive_over_sample_ranges(pipeline):
-    """Same seed -> same bits; splitting the stratum range (what ranks do) changes the sums only by fp32
-    rounding of the accumulation buffer."""
+def test_bit_reproducible_and_additive_over_sample_ranges(pipeline):
+    """"Every render reproducible" (north star): the accumulation buffer holds 64-bit fixed-point sums added with integer
+    atomics, so the image does not depend on the order paths finish in -- same seed -> same BITS, run to run, and for
+    any split of the stratum range over calls (what ranks do), in both pipelines."""
     b = BuiltScene("c5", width=128, spp=64)
     g = Scene(b)
     a, _ = g.render(pipeline=pipeline)
-    a2, _ = g.render(pipeline=pipeline)
-    if pipeline == capi.PIPELINE_MEGAKERNEL:
-        assert np.array_equal(a, a2)
-    else:
-        assert np.allclose(a, a2, rtol=1e-5, atol=1e-4)
+    a2, _ = Scene(b).render(pipeline=pipeline)
+    assert np.array_equal(a, a2)
     parts = np.zeros_like(a)
+    acc = np.zeros_like(a)
     for lo, hi in ((0, 10), (10, 33), (33, 64)):
         g.render(lo, hi, pipeline=pipeline, out=parts)   # accumulates INTO `parts` (Q24)
-    assert np.allclose(parts, a, rtol=2e-6, atol=1e-4)
+    # (the three host-side f64 additions of `parts` round; the device sums themselves are exact -- checked through
+    #  rtb_render_device in test_device_buffers_of_disjoint_ranges_add_up_exactly)
+    assert np.allclose(parts, a, rtol=1e-14, atol=0)
     g2 = Scene(BuiltScene("c5", width=128, spp=64, seed=99))
     c, _ = g2.render(pipeline=pipeline)
     assert not np.array_equal(a, c) and abs(a.mean() - c.mean()) < 0.05 * a.mean()
 
 
-@pytest.mark.parametrize("env", ["RTB_BVH4", "RTB_QNODES"])
+def test_device_buffers_of_disjoint_ranges_add_up_exactly():
+    """rtb_render_device accumulates INTO a caller-owned u64 x 4 buffer: one call over [0, 64) and three calls over a
+    split of it leave the same bits (what makes the multi-GPU int64 reduce split-invariant), whichever pipeline
+    renders which part; counts = strata per pixel."""
+    import torch
+    b = BuiltScene("c3", width=96, spp=64, variant=1)
+    g = Scene(b)
+    h, w = g.info.image_height, g.info.image_width
+    one = torch.zeros((h, w, 4), dtype=torch.int64, device="cuda")
+    g.render_device(one.data_ptr(), 0, 64, pipeline=capi.PIPELINE_WAVEFRONT)
+    torch.cuda.synchronize()
+    split = torch.zeros_like(one)
+    for (lo, hi), pipeline in (((0, 7), capi.PIPELINE_WAVEFRONT), ((7, 40), capi.PIPELINE_WAVEFRONT), ((40, 64), capi.PIPELINE_WAVEFRONT)):
+        g.render_device(split.data_ptr(), lo, hi, pipeline=pipeline)
+    torch.cuda.synchronize()
+    assert torch.equal(one, split) and int(one[..., 3].min()) == int(one[..., 3].max()) == 64
+    px = g.accum_to_pixels(one.data_ptr())
+    ref, _ = g.render(pipeline=capi.PIPELINE_WAVEFRONT)
+    assert np.array_equal(px, ref)
+    assert np.array_equal(px, one[..., :3].cpu().numpy().astype(np.float64) / capi.ACCUM_SCALE)
+
+
+@pytest.mark.parametrize("cfg,variant", [("c4", 0), ("c4", 1), ("c1", 0), ("c3", 0), ("c5", 0)])
+def test_candidate_scheme_renders_the_very_same_image(cfg, variant):
+    """The traversal decides nothing that could change a result: with the f64 tests back inside the traversal
+    (RTB_OPT_EXACT_LEAVES: the round-1 kernel) or the tree's top staged in shared memory (RTB_OPT_SMEM_TOP) every ray
+    finds the same hit, every path is the same path, and the image is the same image BIT FOR BIT."""
+    b = BuiltScene(cfg, width=200, spp=16, variant=variant)
+    ref, st = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    exact, st_e = Scene(b).set_option(capi.OPT_EXACT_LEAVES, 1).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert np.array_equal(ref, exact)
+    assert st["segments"] == st_e["segments"] and st_e["overflow_rays"] == 0
+    assert st["exact_tests"] < 0.75 * st_e["prim_tests"]            # fewer f64 tests, and those at dense lanes
+    assert st["overflow_rays"] < 0.005 * st["segments"]
+    smem, _ = Scene(b).set_option(capi.OPT_SMEM_TOP, 1).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    assert np.array_equal(ref, smem)
+
+
+@pytest.mark.parametrize("flag", [capi.RTB_FLAG_BVH4, capi.RTB_FLAG_QNODES])
 @pytest.mark.parametrize("cfg", ["c4", "c2"])
-def test_opt_in_tree_forms_give_the_same_image(cfg, env, monkeypatch):
+def test_opt_in_tree_forms_give_the_same_image(cfg, flag):
     """The extend kernel's other node formats (collapsed BVH4, 16-bit quantised nodes; chosen when the scene
-    is created) only change the cull: same closest hits, hence the same image up to the order of the fp32
-    atomic adds, and strictly fewer / equally many node visits for the BVH4."""
-    b = BuiltScene(cfg, width=160, spp=16)
-    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-    monkeypatch.setenv(env, "1")
-    alt, st_alt = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-    assert np.allclose(alt, ref, rtol=1e-5, atol=1e-4)
+    is created) only change the cull: same closest hits, hence the same image bit for bit, and strictly fewer
+    node visits for the BVH4."""
+    ref, st_ref = Scene(BuiltScene(cfg, width=160, spp=16)).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    alt, st_alt = Scene(BuiltScene(cfg, width=160, spp=16, flags=flag)).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert np.array_equal(alt, ref)
     assert st_alt["segments"] == st_ref["segments"] and st_alt["prim_tests"] <= 1.1 * st_ref["prim_tests"]
-    if env == "RTB_BVH4":
+    if flag == capi.RTB_FLAG_BVH4:
         assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
 
 
-def test_multi_primitive_leaves_give_the_same_image(monkeypatch):
-    """RTB_BVH_LEAF > 1 (a tuning knob of the builder) makes leaves of several primitives: the extend kernel then
-    runs its generic-leaf instantiation.  Same closest hits, same image; fewer nodes, more primitive tests."""
-    b = BuiltScene("c4", width=160, spp=16)
-    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-    monkeypatch.setenv("RTB_BVH_LEAF", "4")
-    monkeypatch.setenv("RTB_BVH_CI", "0.7")
-    g = Scene(b)
+def test_multi_primitive_leaves_give_the_same_image():
+    """RTB_FLAG_BVH_LEAF4 (a tuning arm of the builder) makes leaves of several primitives: the extend kernel then
+    runs its generic-leaf instantiation and whole leaves travel as candidates.  Same closest hits, same image; fewer
+    nodes, more primitive tests."""
+    ref, st_ref = Scene(BuiltScene("c4", width=160, spp=16)).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    g = Scene(BuiltScene("c4", width=160, spp=16, flags=capi.RTB_FLAG_BVH_LEAF4))
     alt, st = g.render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     assert st["segments"] == st_ref["segments"] and st["prim_tests"] > 1.5 * st_ref["prim_tests"]
     assert st["node_visits"] < st_ref["node_visits"]
-    assert np.allclose(alt, ref, rtol=1e-5, atol=1e-4)
+    # (another shade instantiation -- the generic one -- shades these paths: last-bit FMA differences part a few of them)
+    rel = np.abs(alt - ref).max(axis=2) / (np.abs(ref).max(axis=2) + 1e-3)
+    assert (rel > 1e-3).mean() < 2e-3 and abs(alt.mean() - ref.mean()) < 1e-5 * ref.mean()
     rays = g.camera_rays()[::7]
-    hb, hg = g.trace(rays, capi.RTB_TRACE_BRUTE_FORCE), g.trace(rays)
+    hb, hg, hw = g.trace(rays, capi.RTB_TRACE_BRUTE_FORCE), g.trace(rays), g.trace(rays, capi.RTB_TRACE_WAVEFRONT)
     assert (hb["prim"] == hg["prim"]).all() and np.array_equal(hb["t"], hg["t"])
+    assert (hb["prim"] == hw["prim"]).all() and np.array_equal(hb["t"], hw["t"])
 
 
-def test_deferred_textured_classes_give_the_same_image(monkeypatch):
+def test_deferred_textured_classes_give_the_same_image():
     """By default the image / Perlin Lambertian items are shaded by k_wf_shade_rare from a deferred list and the
-    main shade kernel carries no texture code; RTB_WF_DEFER_RARE=0 shades everything in place.  Same paths, same
-    image (fp32 atomic order aside) -- on the scene with both textured spheres, with and without a light list."""
+    main shade kernel carries no texture code; RTB_OPT_NO_DEFER_RARE shades everything in place.  Same rays, same
+    hits -- on the scene with both textured spheres, with and without a light list."""
     for variant in (0, 1):
         b = BuiltScene("c4", width=200, spp=16, variant=variant)
         on, st_on = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
-        monkeypatch.setenv("RTB_WF_DEFER_RARE", "0")
-        off, st_off = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
-        monkeypatch.delenv("RTB_WF_DEFER_RARE")
+        off, st_off = Scene(b).set_option(capi.OPT_NO_DEFER_RARE, 1).render(pipeline=capi.PIPELINE_WAVEFRONT)
         assert st_on["kernel_launches"] > st_off["kernel_launches"]      # the extra k_wf_shade_rare per iteration
-        # the textured items run through another instantiation of the same fp32 shading code (other FMA
-        # contraction): a few paths in 10^5 differ in the last bits and then part ways (measured: 0.02 % of the
-        # pixels beyond 1e-4 relative, largest difference 7e-4, means equal to 7 digits)
+        # The two arms shade through different instantiations of the same fp32 code (other FMA contraction): a path
+        # whose sampled direction differs in the last bit may later cross a discontinuity and part ways.  Measured
+        # per cause below: the pixels that differ at all, and those beyond 1e-3 relative.
         rel = np.abs(on - off).max(axis=2) / (np.abs(off).max(axis=2) + 1e-3)
+        print(f"variant {variant}: pixels that differ {(on != off).any(axis=2).mean():.4f}, beyond 1e-5 {(rel > 1e-5).mean():.5f}, "
+              f"beyond 1e-3 {(rel > 1e-3).mean():.5f}, max {rel.max():.2e}, means {on.mean():.9f} {off.mean():.9f}")
         assert (rel > 1e-3).mean() < 2e-3 and abs(on.mean() - off.mean()) < 1e-5 * off.mean(), ((rel > 1e-3).mean(), on.mean(), off.mean())
     # a scene whose only textured material is NOT a plain Lambertian surface must not defer: simple_light's
     # textures are Perlin spheres + solid lights (defers), two_perlin_spheres too; furnace-like scenes have none
@@ -215,38 +348,116 @@ def test_deferred_textured_classes_give_the_same_image(monkeypatch):
     assert (rel > 2e-3).mean() < 0.01 and abs(on.mean() - mega.mean()) < 2e-3 * mega.mean()
 
 
-def test_tma_staged_shade_kernel_gives_the_same_image(monkeypatch):
-    """The opt-in persistent shade kernel (cp.async.bulk tiles on an mbarrier, index sort) is the same
-    computation as the default one: same paths, same segments, same image up to fp32 atomic order --
-    also across partial last tiles and many tiles per block (small queue)."""
-    b = BuiltScene("c4", width=160, spp=16, variant=1)
-    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-    monkeypatch.setenv("RTB_WF_SHADE_TMA", "1")
-    for cap in (None, 5000):
-        if cap:
-            monkeypatch.setenv("RTB_WF_CAPACITY", str(cap))
-        alt, st = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-        assert abs(st["segments"] - st_ref["segments"]) <= 1e-5 * st_ref["segments"]
-        # (another instantiation of the same fp32 shading code: a few paths in 10^5 may differ in the last bits)
-        rel = np.abs(alt - ref).max(axis=2) / (np.abs(ref).max(axis=2) + 1e-3)
-        assert (rel > 1e-3).mean() < 2e-3 and abs(alt.mean() - ref.mean()) < 1e-5 * ref.mean()
-
-
 @pytest.mark.parametrize("capacity", [1024, 5000, 65536])
-def test_small_queues_refill_and_drain_to_the_same_image(capacity, monkeypatch):
+def test_small_queues_refill_and_drain_to_the_same_image(capacity):
     """The wavefront queue is topped up every iteration and its launches shrink with the draining tail; a queue
     far smaller than the job (down to the 1024-slot minimum, and a size that is no multiple of a block)
     exercises every refill / partial-block / tail-sizing path.  Philox keys make the image independent of
-    the schedule, up to the order of the fp32 atomic adds."""
+    the schedule -- bit for bit, now that the accumulation does not depend on the order of the adds."""
     b = BuiltScene("c3", width=96, spp=36, variant=1)
-    g = Scene(b)
+    g = Scene(b).set_option(capi.OPT_FINISH_BELOW, 0)
     ref, st_ref = g.render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     mega, _ = g.render(pipeline=capi.PIPELINE_MEGAKERNEL)
-    monkeypatch.setenv("RTB_WF_CAPACITY", str(capacity))
-    small, st = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    small, st = Scene(b).set_option(capi.OPT_WF_CAPACITY, capacity).set_option(capi.OPT_FINISH_BELOW, 0).render(
+        pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     assert st["paths"] == st_ref["paths"] and st["segments"] == st_ref["segments"]
     assert st["kernel_launches"] > st_ref["kernel_launches"]
-    assert np.allclose(small, ref, rtol=1e-5, atol=1e-4) and np.allclose(small, mega, rtol=1e-4, atol=1e-3)
+    assert np.array_equal(small, ref) and np.allclose(small, mega, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c3", "c4"])
+def test_finishing_kernel_ends_the_tail_with_the_same_paths(cfg):
+    """Once every path has started and few are left (RTB_OPT_FINISH_BELOW, default 65536), k_wf_finish runs each of them
+    to its end instead of ~40 more iterations of launches: same segments; same image up to the last-bit differences
+    between the shade instantiations (a few paths part ways), far fewer launches on a depth-50 scene."""
+    b = BuiltScene(cfg, width=240, spp=16)
+    loop, st_loop = Scene(b).set_option(capi.OPT_FINISH_BELOW, 0).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    fin, st_fin = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert st_fin["kernel_launches"] < st_loop["kernel_launches"]
+    assert abs(st_fin["segments"] - st_loop["segments"]) <= 1e-4 * st_loop["segments"]
+    rel = np.abs(fin - loop).max(axis=2) / (np.abs(loop).max(axis=2) + 1e-3)
+    assert (rel > 1e-3).mean() < 2e-3 and abs(fin.mean() - loop.mean()) < 1e-5 * loop.mean(), ((rel > 1e-3).mean(), fin.mean(), loop.mean())
+    always, st_a = Scene(b).set_option(capi.OPT_FINISH_BELOW, 1 << 24).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert abs(st_a["segments"] - st_loop["segments"]) <= 1e-4 * st_loop["segments"]
+    rel = np.abs(always - loop).max(axis=2) / (np.abs(loop).max(axis=2) + 1e-3)
+    assert (rel > 1e-3).mean() < 5e-3 and abs(always.mean() - loop.mean()) < 1e-4 * loop.mean()
+
+
+def test_small_calls_take_the_megakernel_and_depth_zero_traces_nothing():
+    """RTB_PIPELINE_DEFAULT: below 2^19 paths per call the wavefront is launch-bound and the megakernel renders the
+    call (one launch); max_depth 0 returns black like ray_color's `depth <= 0` (render.rs:260-262), max_depth 1 sees
+    emitters and background only -- both as the oracle has them."""
+    b = BuiltScene("c5", width=64, spp=16)
+    g = Scene(b)
+    _, st = g.render()
+    assert st["kernel_launches"] == 1
+    _, st = g.render(pipeline=capi.PIPELINE_WAVEFRONT)
+    assert st["kernel_launches"] > 4
+    _, st = Scene(b).set_option(capi.OPT_MEGA_BELOW, 0).render()
+    assert st["kernel_launches"] > 4
+    for cfg in ("c5", "c1"):
+        for depth in (0, 1):
+            bd = BuiltScene(cfg, width=64, spp=16, depth=depth) if depth else None
+            if depth == 0:
+                bd = BuiltScene(cfg, width=64, spp=16)
+                bd.desc.contents.camera.max_depth = 0
+            so, _ = orc.OracleScene(bd).render(sampler=orc.SAMPLER_KEYED)
+            for pipeline in PIPELINES:
+                sg, stg = Scene(bd).render(pipeline=pipeline)
+                assert stg["paths"] == 64 * sg.shape[0] * 16
+                if depth == 0:
+                    assert not sg.any() and not so.any()
+                else:
+                    assert np.allclose(sg, so, rtol=1e-5, atol=1e-6), (cfg, depth, pipeline)
+
+
+def test_sun_light_flag_and_auto_exposure_against_the_oracle():
+    """scene_sun_spheres (reference src/main.rs:32-90, scene -2): `suns` is ignored at HEAD (Q23) -- with and without
+    the sun records the image is the same -- and RTB_FLAG_SUN_LIGHT restores the commented-out term `background +
+    sun_light` (render.rs:300-308) exactly as the oracle restates it.  auto_expose (render.rs:325-339) of the sums and
+    the exposed write_color bytes equal the oracle's."""
+    b_off = BuiltScene("scene_sun_spheres", width=160, spp=16)
+    b_on = BuiltScene("scene_sun_spheres", width=160, spp=16, flags=capi.RTB_FLAG_SUN_LIGHT)
+    assert b_on.desc.contents.n_suns == 1
+    off, _ = Scene(b_off).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    no_suns = BuiltScene("scene_sun_spheres", width=160, spp=16)
+    no_suns.desc.contents.n_suns = 0
+    assert np.array_equal(off, Scene(no_suns).render(pipeline=capi.PIPELINE_WAVEFRONT)[0])
+    so, _ = orc.OracleScene(b_on).render(sampler=orc.SAMPLER_KEYED)
+    for pipeline in PIPELINES:
+        on, _ = Scene(b_on).render(pipeline=pipeline)
+        assert on.mean() > 1.3 * off.mean()
+        rel = np.abs(so - on).max(axis=2) / (np.abs(so).max(axis=2) + 1e-3)
+        assert (rel > 2e-3).mean() < 0.02 and abs(so.mean() - on.mean()) < 3e-3 * so.mean(), (pipeline, (rel > 2e-3).mean())
+    from surely_raytracing_b200 import auto_expose
+    e_g, e_o = auto_expose(on, 16), orc.auto_expose(on, 16)
+    assert e_g == e_o and 0.05 < e_g < 50 and e_g != 1.0
+    g = Scene(b_on)
+    assert np.array_equal(g.write_color(on, 16, e_g), orc.write_color(on, 16, e_o))
+    assert auto_expose(np.zeros((8, 8, 3)), 4) == 1.0 == orc.auto_expose(np.zeros((8, 8, 3)), 4)
+
+
+def test_render_multi_is_the_same_image_on_any_number_of_gpus():
+    """rtb_render_multi = the reference seam on one box: contiguous slices of the stratum range on n GPUs (one thread,
+    scene copy and stream each), ONE NCCL int64 sum-reduce, one D2H.  The image must not depend on n: bit-identical to
+    rtb_render on one GPU (runs with every device count the box has, 1 included)."""
+    from surely_raytracing_b200 import render_multi
+    lib = capi.load_library()
+    n_gpu = lib.rtb_device_count()
+    b = BuiltScene("c4", width=200, spp=64, variant=1)
+    ref, st_ref = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    for n in sorted({1, 2, n_gpu} & set(range(1, n_gpu + 1))):
+        px, st = render_multi(b, n, pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+        assert np.array_equal(px, ref), n
+        assert st["paths"] == st_ref["paths"] and st["segments"] == st_ref["segments"]
+    out = np.full_like(ref, 1.5)
+    render_multi(b, 1, out=out)
+    assert np.array_equal(out, ref + 1.5) or np.allclose(out, ref + 1.5, rtol=1e-15)
+    with pytest.raises(capi.RtbError):
+        render_multi(b, n_gpu + 1)
+    with pytest.raises(capi.RtbError):
+        render_multi(b, 1, 0, 10 ** 6)
+    assert lib.rtb_trim_cache() > 0
 
 
 def test_flags_iso_pdf_zero_and_full_size_round_trip_property():
@@ -289,8 +500,7 @@ def test_cpp_drop_in_example_writes_the_same_ppm_as_the_python_path(tmp_path):
     g = Scene(BuiltScene("c5", width=64, spp=16))
     s, _ = g.render()
     ours = g.write_color(s, g.info.spp_used)
-    # wavefront accumulation order is not fixed (float atomics): allow the last digit to move
-    assert np.abs(ppm.astype(int) - ours.astype(int)).max() <= 1 and (ppm != ours).mean() < 0.01
+    assert np.array_equal(ppm, ours)                         # same seed, same pipeline choice, order-independent sums
 
 
 @pytest.mark.parametrize("name", ["scene_three_spheres", "two_spheres", "earth", "two_perlin_spheres", "quads", "simple_light"])

@@ -103,7 +103,7 @@ long long sim_collect(void* p, int cap, long long s_begin, long long s_end, int 
     if (iter + 1 >= it_hi) break;
     // extend + block-sorted shade
     std::vector<Event> evs(in.size());
-    DStats st = {0, 0, 0, 0, 0, 0};
+    DStats st = {};
     for (size_t i = 0; i < in.size(); i++) extend<false>(S, in[i], evs[i], &st);
     for (size_t b0 = 0; b0 < in.size(); b0 += 256) {
       const size_t b1 = std::min(in.size(), b0 + 256);
@@ -498,7 +498,7 @@ extern "C" int sim_candidates(void* p, const QRay* rays, long long n, int K, dou
     r.dx = rays[i].dx; r.dy = rays[i].dy; r.dz = rays[i].dz; r.time = rays[i].time;
     Hit exact;
     hit_reset(exact);
-    DStats st = {0, 0, 0, 0, 0, 0}, sc = {0, 0, 0, 0, 0, 0};
+    DStats st = {}, sc = {};
     closest_surface<true>(S, r, 0.0001, exact, &st);
     Cands C;
     const bool ok = closest_candidates<true>(S, r, S.scene_mag, C, &sc);
