@@ -82,6 +82,7 @@ def parse_args():
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c2/c3/c5 block")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--option", action="append", default=[], help="RTB_OPT id=value (tuning / A-B runs), e.g. 2=1 for exact leaves")
+    ap.add_argument("--flags", type=lambda v: int(v, 0), default=0, help="RTB_FLAG_* bits of the scene description (builder arms)")
     ap.add_argument("--curve", action="store_true", help="variance-vs-time curve (BASELINE config 5): RMSE vs the oracle at growing spp")
     return ap.parse_args()
 
@@ -350,7 +351,7 @@ def run_b200(args, rank, world, local_rank):
             run_curve(args, dev, torch)
         return
 
-    built = BuiltScene(args.workload, width=args.width)
+    built = BuiltScene(args.workload, width=args.width, flags=args.flags)
     t0 = time.perf_counter()
     scene = apply_options(Scene(built, device=local_rank), args)
     upload_ms = (time.perf_counter() - t0) * 1e3

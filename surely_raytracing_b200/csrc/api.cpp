@@ -158,6 +158,7 @@ struct rtb_scene {
   size_t upload_bytes = 0;
   CachedBuffer workspace;  // wavefront queues (leased from the process-wide cache)
   CachedBuffer staging;    // pinned host staging of the f64 sums
+  CachedBuffer sums;       // device f64 sums on their way to the host (cached: a cudaFree per scene costs a device sync)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   WavefrontContext wf{};
   bool wf_ready = false;
@@ -359,10 +360,10 @@ int fetch_stats(rtb_scene* s, RtbStats* stats) {
 // device accumulation buffer -> += host f64 sums (`row[i] = row[i] + color`, Q24)
 int accum_to_host(rtb_scene* s, const unsigned long long* d_accum, double* pixels_rgb, cudaStream_t stream) {
   const size_t n = (size_t)s->host->cam.width * s->host->cam.height;
-  CU(s->scratch_a.reserve(n * 3 * sizeof(double)));
+  CU(s->sums.reserve(s->device, 7, n * 3 * sizeof(double), false));
   CU(s->staging.reserve(s->device, 3, n * 3 * sizeof(double), true));
-  CU(launch_accum_to_f64(d_accum, (int64_t)n, static_cast<double*>(s->scratch_a.p), 0, stream));
-  CU(cudaMemcpyAsync(s->staging.p, s->scratch_a.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CU(launch_accum_to_f64(d_accum, (int64_t)n, static_cast<double*>(s->sums.p), 0, stream));
+  CU(cudaMemcpyAsync(s->staging.p, s->sums.p, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
   const double* h = static_cast<const double*>(s->staging.p);
   for (size_t i = 0; i < 3 * n; i++) pixels_rgb[i] += h[i];

@@ -128,6 +128,7 @@ struct DMedium {
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
   float diag;               // diagonal of that box: no chord of the boundary is longer
   float pad;
+  float sphere[4];          // boundary = one static sphere (cls_fast bit 8): centre, and r^2 shrunk by 1e-3 relative (inside test)
 };
 
 struct alignas(32) DLight {

@@ -726,7 +726,15 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     Box bx;
     for (const Baked& b : B.boundaries[mi]) { emit_prim(d, out, b); bx.grow(b.lo, b.hi); }
     m.cls_fast = shading_class(d, m.material);
-    if (m.n_prims == 1 && B.boundaries[mi][0].kind == PRIM_SPHERE && !(B.boundaries[mi][0].flags & PRIM_FLAG_MOVING)) m.cls_fast |= 0x100;
+    if (m.n_prims == 1 && B.boundaries[mi][0].kind == PRIM_SPHERE && !(B.boundaries[mi][0].flags & PRIM_FLAG_MOVING)) {
+      m.cls_fast |= 0x100;
+      const double* sp = B.boundaries[mi][0].payload;  // cx cy cz r
+      for (int a = 0; a < 3; a++) m.sphere[a] = (float)sp[a];
+      // fp32 evaluation of |p - c|^2 at scene magnitude M errs by ~1e-6 (M + r)^2; 1e-3 r^2 covers it for r >= M / 20,
+      // a smaller sphere loses the shortcut near its surface only (the margin below is then subtracted explicitly)
+      const double r2 = sp[3] * sp[3];
+      m.sphere[3] = round_down(std::max(0., r2 * (1. - 1e-3) - 4e-6 * (M + std::fabs(sp[3])) * (M + std::fabs(sp[3]))));
+    }
     {
       bool all_quads = m.n_prims > 0;
       for (const Baked& b : B.boundaries[mi]) all_quads = all_quads && b.kind == PRIM_QUAD;

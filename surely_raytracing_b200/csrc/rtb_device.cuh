@@ -471,12 +471,14 @@ struct PfRay {
   float dd;       // d . d
   float num_err;  // bound of the f64 rounding of d - n.o and o - q for this origin (4e-13 x coordinate magnitude)
 };
+// scene_mag bounds every coordinate in play (primitives, camera, and -- for the parity harness, whose rays may start
+// anywhere -- the ray origins of the call): |d| + sum |n_i o_i| <= 4 scene_mag, times 500 x the f64 unit roundoff
 RTB_DEV PfRay pf_ray(double ox, double oy, double oz, float dx, float dy, float dz, float time, float scene_mag) {
   PfRay r;
   r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.time = time;
   r.d1 = fabsf(dx) + fabsf(dy) + fabsf(dz);
   r.dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-  r.num_err = 4e-13f * (scene_mag + fabsf((float)ox) + fabsf((float)oy) + fabsf((float)oz));
+  r.num_err = 2e-12f * scene_mag;
   return r;
 }
 
@@ -563,8 +565,8 @@ RTB_DEV int prefilter_sphere(const double2* __restrict__ P, bool moving, const P
   const double ocx64 = r.ox - cx, ocy64 = r.oy - cy, ocz64 = r.oz - cz;
   const float ocx = (float)ocx64, ocy = (float)ocy64, ocz = (float)ocz64;
   const float cc = (float)fma(-cr.d, cr.d, fma(ocz64, ocz64, fma(ocy64, ocy64, ocx64 * ocx64)));
-  const float rad = (float)cr.d;
-  const float cc_err = 4e-15f * fmaf(2.f * rad, rad, fabsf(cc)) + 1e-30f;  // f64 rounding of |oc|^2 - r^2 (both sides')
+  // f64 rounding of |oc|^2 - r^2 (the reference's and ours): 4e-15 (|oc|^2 + r^2), with r^2 = |oc|^2 - cc
+  const float cc_err = 4e-15f * fmaf(2.1f, fmaf(ocx, ocx, fmaf(ocy, ocy, ocz * ocz)), fabsf(cc)) + 1e-30f;
   const float hb = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
   const float hb_err = 10.f * PF_U * fmaf(fabsf(ocx), fabsf(r.dx), fmaf(fabsf(ocy), fabsf(r.dy), fabsf(ocz * r.dz))) + 1e-30f;
   const float ac = r.dd * cc;
@@ -800,7 +802,22 @@ RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, dou
     if (hit_distance > bound * (1. + 1e-9) + 1e-12) return RTB_INF;
   }
   double t1, t2;
-  if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2)) return RTB_INF;
+  bool inside = false;
+  if ((m.cls_fast & 0x100) && tmax < RTB_INF) {
+    // Boundary = one static sphere and the clamped segment [tmin, tmax] lies wholly inside it (both end points do,
+    // by a wide fp32 margin; a ball is convex): then root1 < 0 < tmin and root2 > tmax, both probes of
+    // constant_medium.rs:46-55 succeed, and the clamps below turn the interval into [tmin, tmax] whatever the
+    // roots are -- the same value without evaluating them.  (The book-2 fog of radius 5000 contains every segment
+    // that ends on a surface: two f64 divisions and a square root per probe, gone.)
+    const float ax = (float)r.ox - m.sphere[0], ay = (float)r.oy - m.sphere[1], az = (float)r.oz - m.sphere[2];
+    const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz, ta = (float)tmin, tb = (float)tmax;
+    const float pa = fmaf(ta, dx, ax), qa = fmaf(ta, dy, ay), ra = fmaf(ta, dz, az);
+    const float pb = fmaf(tb, dx, ax), qb = fmaf(tb, dy, ay), rb = fmaf(tb, dz, az);
+    const float da = fmaf(pa, pa, fmaf(qa, qa, ra * ra)), db = fmaf(pb, pb, fmaf(qb, qb, rb * rb));
+    inside = da < m.sphere[3] && db < m.sphere[3];  // sphere[3] = r^2 shrunk by 1e-3 relative (flatten.cpp)
+  }
+  if (inside) { t1 = -RTB_INF; t2 = RTB_INF; }
+  else if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2)) return RTB_INF;
   if (t1 < tmin) t1 = tmin;   // :58-60
   if (t2 > tmax) t2 = tmax;   // :61-63
   if (t1 >= t2) return RTB_INF;

@@ -199,11 +199,13 @@ __device__ __forceinline__ void wf_advance(const WFQueues& Q) {
 __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DScene S, WFQueues Q, long long s_begin,
                                                       RayRec* __restrict__ out) {
   WFCounters* c = Q.c;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long next_path = c->next_path;
   const unsigned long long left = c->total_paths - next_path;
   const int n_out = c->n_out;
-  if (i < Q.capacity - n_out && (unsigned long long)i < left) {
+  // grid-stride over the free slots: the grid is capped (one arrival atomic per block below: 131 K blocks arriving
+  // on one address cost 0.14 ms per iteration when the grid was sized to the queue)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Q.capacity - n_out && (unsigned long long)i < left;
+       i += (long long)gridDim.x * blockDim.x) {
     const unsigned long long pid = next_path + (unsigned long long)i;
     const uint32_t tiles_x = (uint32_t)(S.cam.width + 7) >> 3;
     const uint32_t tiles = tiles_x * (uint32_t)((S.cam.height + 3) >> 2);
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const __grid_constant__ DSc
     }
     p.sample = sample;
     const RayRec rec = pack_primary(p);
-    const int o = n_out + i, cap = Q.capacity;
+    const int o = n_out + (int)i, cap = Q.capacity;
     st_stream(ray_plane(out, cap, 0) + o, rec.a); st_stream(ray_plane(out, cap, 1) + o, rec.b);
     st_stream(ray_plane(out, cap, 2) + o, rec.c); st_stream(ray_plane(out, cap, 3) + o, rec.d);
   }
@@ -260,8 +262,17 @@ constexpr int TRAV_DONE = 0x7FFFFFFF;
 #ifndef WF_BREAK_LEFT
 #define WF_BREAK_LEFT 16  // measured on c4: 0 -> 35.1, 12 -> 33.9, 16 -> 33.4, 20 -> 33.5, 24 -> 33.8 ms extend per step
 #endif
+#ifndef WF_BREAK_RELATIVE
+#define WF_BREAK_RELATIVE 0
+#endif
+#ifndef WF_SYNC_AFTER_LEAVES
+#define WF_SYNC_AFTER_LEAVES 1
+#endif
 #ifndef WF_EXTEND_MIN_BLOCKS_CAND
-#define WF_EXTEND_MIN_BLOCKS_CAND 8
+#define WF_EXTEND_MIN_BLOCKS_CAND 9  // 36 warps per SM at 56 registers (16 B of spills); measured on c4: 8 -> 264.4, 9 -> 255.0, 10 -> 301 ms extend per step
+#endif
+#ifndef WF_PREFETCH_AHEAD
+#define WF_PREFETCH_AHEAD 0  // queue positions ahead of the fetch cursor to pull into L2 (0 = off)
 #endif
 
 // NODES: which form of the tree is traversed, chosen per scene by the builder --
@@ -316,6 +327,14 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
         const int leader = __ffs(need) - 1;
         if (lane == leader) base = atomicAdd(&Q.c->extend_cursor, __popc(need));
         base = __shfl_sync(FULL, base, leader);
+#if WF_PREFETCH_AHEAD > 0
+        // the queue is streamed front to back by all warps together: ask the L2 for the lines the cursor reaches soon
+        // (3 planes x up to 4 lines of 128 B cover the <= 32 positions of one fetch)
+        if (lane < 12) {
+          const int kp = base + WF_PREFETCH_AHEAD + (lane & 3) * 8;
+          if (kp < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(ray_plane(rays_in, Q.capacity, lane >> 2) + kp));
+        }
+#endif
         if (!have && !exhausted) {
           const int k = base + __popc(need & ((1u << lane) - 1u));
           if (k < n) {
@@ -425,7 +444,11 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
       const unsigned looping = __activemask();
       if (!__any_sync(looping, leaf == 0)) break;
 #if WF_BREAK_LEFT > 0
+#if WF_BREAK_RELATIVE
+      if (5 * __popc(looping) < 2 * entered) break;  // fewer than 40 % of the lanes that entered are still descending
+#else
       if (entered - __popc(looping) >= WF_BREAK_LEFT) break;
+#endif
 #endif
     }
     // ---- leaves: the postponed one, then the current node if it is a leaf too -------------------------
@@ -459,6 +482,13 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
       }
       if (have) tbest32 = __double2float_ru(best.t);
     }
+#if WF_SYNC_AFTER_LEAVES
+    // The lanes leave the leaf phase in groups (no leaf / quad / sphere / second leaf).  Without an explicit
+    // reconvergence point ptxas let each group run on to the loop top on its own (ncu: the block below and the
+    // fetch prologue executed 3.8 M times at 9 lanes instead of 1.3 M times at 32, and every __ballot_sync went
+    // through an out-of-line WARPSYNC.COLLECTIVE path).
+    __syncwarp();
+#endif
     if (have && node == TRAV_DONE) {
       int2 h;
       if (CAND) {
@@ -919,7 +949,7 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
   const long long finish_below = opt.finish_below >= 0 ? opt.finish_below : 65536;
   bool finished = false;
   for (long long iter = 0;; iter++) {
-    const unsigned gen_blocks = (unsigned)((bound + 255) / 256);
+    const unsigned gen_blocks = (unsigned)std::min<long long>((bound + 255) / 256, (long long)ctx.sms * 8);
     const unsigned shade_blocks = (unsigned)((bound + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK);
     const unsigned extend_grid = (unsigned)std::min<long long>(extend_grid_full, (bound + WF_EXTEND_BLOCK - 1) / WF_EXTEND_BLOCK);
     // top the out queue up (first iteration: fill it), then it becomes this iteration's in queue

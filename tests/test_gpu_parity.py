@@ -287,8 +287,12 @@ def test_candidate_scheme_renders_the_very_same_image(cfg, variant):
     assert st["segments"] == st_e["segments"] and st_e["overflow_rays"] == 0
     assert st["exact_tests"] < 0.75 * st_e["prim_tests"]            # fewer f64 tests, and those at dense lanes
     assert st["overflow_rays"] < 0.005 * st["segments"]
-    smem, _ = Scene(b).set_option(capi.OPT_SMEM_TOP, 1).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    smem, _ = Scene(b).set_option(capi.OPT_SMEM_TOP, 1).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     assert np.array_equal(ref, smem)
+    # ... and in the uncounted (scene-specialised) instantiations that production calls run
+    ref2, _ = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    exact2, _ = Scene(b).set_option(capi.OPT_EXACT_LEAVES, 1).render(pipeline=capi.PIPELINE_WAVEFRONT)
+    assert np.array_equal(ref2, exact2)
 
 
 @pytest.mark.parametrize("flag", [capi.RTB_FLAG_BVH4, capi.RTB_FLAG_QNODES])
@@ -373,7 +377,9 @@ def test_finishing_kernel_ends_the_tail_with_the_same_paths(cfg):
     b = BuiltScene(cfg, width=240, spp=16)
     loop, st_loop = Scene(b).set_option(capi.OPT_FINISH_BELOW, 0).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     fin, st_fin = Scene(b).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
-    assert st_fin["kernel_launches"] < st_loop["kernel_launches"]
+    assert st_fin["kernel_launches"] <= st_loop["kernel_launches"]
+    if cfg == "c1":                                                   # depth 50: dozens of nearly empty iterations saved
+        assert st_fin["kernel_launches"] < 0.7 * st_loop["kernel_launches"]
     assert abs(st_fin["segments"] - st_loop["segments"]) <= 1e-4 * st_loop["segments"]
     rel = np.abs(fin - loop).max(axis=2) / (np.abs(loop).max(axis=2) + 1e-3)
     assert (rel > 1e-3).mean() < 2e-3 and abs(fin.mean() - loop.mean()) < 1e-5 * loop.mean(), ((rel > 1e-3).mean(), fin.mean(), loop.mean())

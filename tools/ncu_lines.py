@@ -52,7 +52,7 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     blocks = raw.split('"Kernel Name",')
     root = Path(__file__).resolve().parent.parent / "surely_raytracing_b200" / "csrc"
-    ranges = {p.name: function_ranges(p) for p in [root / "rtb_device.cuh", root / "kernels.cu"]}
+    ranges = {p.name: function_ranges(p) for p in [root / "rtb_device.cuh", root / "kernels.cu", root / "wavefront.cu"]}
     lm_all = line_map(so, ksub)
     for blk in blocks[1:]:
         kname, rest = blk.split("\n", 1)
