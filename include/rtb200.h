@@ -332,6 +332,9 @@ int rtb_write_color(rtb_scene* scene, const double* pixels_rgb, int64_t n_pixels
 /* auto_expose (src/render.rs:325-339): exposure value for write_color from the f64 sums, evaluated on the host
  * in the reference's own sequential order (a serial f64 sum: any other order moves the last bit). */
 int rtb_auto_expose(const double* pixels_rgb, int64_t n_pixels, double spp, double* exposure_out);
+/* KAT hook: Dielectric::scatter (src/material.rs:167-191: Schlick reflectance :156-163, reflect / refract src/vec3.rs:219-229)
+ * on the device.  in9 = n x {direction[3], face normal[3], front_face (0/1), ir, uniform draw}; dir_out = n x 3. */
+int rtb_eval_dielectric(rtb_scene* scene, const double* in9, int64_t n, double* dir_out);
 /* Random123 known-answer hook for the DEVICE copy of Philox4x32-10: ctr_key = n x {c0,c1,c2,c3,k0,k1}, out = n x 4 */
 int rtb_philox(rtb_scene* scene, const uint32_t* ctr_key, int64_t n, uint32_t* out);
 

@@ -1361,6 +1361,26 @@ int orc_write_color(const double* pixels_rgb, int64_t n_pixels, double spp, doub
   return RTB_OK;
 }
 
+// KAT hook: the direction Dielectric::scatter produces (src/material.rs:167-191) for a given uniform draw.
+// in = n x {direction[3], face normal[3], front_face, ir, U}
+int orc_eval_dielectric(const double* in9, int64_t n, double* dir_out) {
+  for (int64_t i = 0; i < n; i++) {
+    const double* a = in9 + 9 * i;
+    const Vec3 r_in(a[0], a[1], a[2]), normal(a[3], a[4], a[5]);
+    const bool front_face = a[6] != 0.;
+    const double ir = a[7], U = a[8];
+    double refraction_ratio = front_face ? 1.0 / ir : ir;
+    Vec3 unit_direction = unit_vector(r_in);
+    double cos_theta = std::fmin(dot(-unit_direction, normal), 1.);
+    double sin_theta = std::sqrt(1.0 - cos_theta * cos_theta);
+    bool cannot_refract = refraction_ratio * sin_theta > 1.0;
+    Vec3 direction = (cannot_refract || dielectric_reflectance(cos_theta, refraction_ratio) > U)
+                         ? reflect(unit_direction, normal) : refract(unit_direction, normal, refraction_ratio);
+    dir_out[3 * i] = direction.x; dir_out[3 * i + 1] = direction.y; dir_out[3 * i + 2] = direction.z;
+  }
+  return RTB_OK;
+}
+
 // auto_expose  src/render.rs:325-339
 double orc_auto_expose(const double* pixels_rgb, int64_t n_pixels, double samples_per_pixel) {
   const double medium_weight = 1. / (double)n_pixels;  // 1 / (image_height * image_width)

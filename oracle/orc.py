@@ -56,6 +56,7 @@ def load():
         lib.orc_sphere_uv.argtypes = [vp, vp]; lib.orc_sphere_uv.restype = None
         lib.orc_philox.argtypes = [vp, vp, vp]; lib.orc_philox.restype = None
         lib.orc_write_color.argtypes = [vp, i64, C.c_double, C.c_double, vp]
+        lib.orc_eval_dielectric.argtypes = [vp, i64, vp]
         lib.orc_auto_expose.argtypes = [vp, i64, C.c_double]; lib.orc_auto_expose.restype = C.c_double
         _lib = lib
     return _lib
@@ -171,3 +172,10 @@ def auto_expose(pixels, spp):
     """auto_expose (reference src/render.rs:325-339) over f64 pixel sums"""
     px = np.ascontiguousarray(pixels, dtype=np.float64)
     return float(load().orc_auto_expose(_ptr(px), px.size // 3, float(spp)))
+
+
+def eval_dielectric(in9):
+    a = np.ascontiguousarray(in9, dtype=np.float64).reshape(-1, 9)
+    out = np.zeros((len(a), 3))
+    load().orc_eval_dielectric(_ptr(a), len(a), _ptr(out))
+    return out

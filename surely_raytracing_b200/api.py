@@ -53,6 +53,13 @@ class Scene:
         capi.check(self._lib, self._lib.rtb_accum_to_pixels(self._h, C.c_void_p(d_accum_ptr), _ptr(out)), "rtb_accum_to_pixels")
         return out
 
+    def eval_dielectric(self, in9: np.ndarray) -> np.ndarray:
+        """Dielectric::scatter on the device: n x {d[3], face normal[3], front, ir, u} -> n x direction[3]"""
+        a = np.ascontiguousarray(in9, dtype=np.float64).reshape(-1, 9)
+        out = np.zeros((len(a), 3))
+        capi.check(self._lib, self._lib.rtb_eval_dielectric(self._h, _ptr(a), len(a), _ptr(out)), "rtb_eval_dielectric")
+        return out
+
     def philox(self, ctr_key: np.ndarray) -> np.ndarray:
         """the device's Philox4x32-10 on n x {c0,c1,c2,c3,k0,k1} (Random123 known-answer hook)"""
         ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)

@@ -119,7 +119,7 @@ EXPORTS = ["rtb_version", "rtb_device_count", "rtb_last_error", "rtb_scene_creat
            "rtb_scene_info", "rtb_render", "rtb_render_device", "rtb_render_stats", "rtb_trace",
            "rtb_camera_rays", "rtb_medium_interval", "rtb_eval_texture", "rtb_eval_light_pdf",
            "rtb_write_color", "rtb_accum_to_pixels", "rtb_render_multi", "rtb_scene_set_option", "rtb_trim_cache",
-           "rtb_auto_expose", "rtb_philox"]
+           "rtb_auto_expose", "rtb_philox", "rtb_eval_dielectric"]
 
 
 class RtbError(RuntimeError):
@@ -162,6 +162,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.rtb_trim_cache.restype = i64
     lib.rtb_auto_expose.argtypes = [vp, i64, C.c_double, C.POINTER(C.c_double)]
     lib.rtb_philox.argtypes = [vp, vp, i64, vp]
+    lib.rtb_eval_dielectric.argtypes = [vp, vp, i64, vp]
     if path is None:
         _lib = lib
     return lib

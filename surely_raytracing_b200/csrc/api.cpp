@@ -803,6 +803,20 @@ int rtb_auto_expose(const double* pixels_rgb, int64_t n_pixels, double spp, doub
   return RTB_OK;
 }
 
+int rtb_eval_dielectric(rtb_scene* s, const double* in9, int64_t n, double* dir_out) {
+  return guarded([&]() -> int {
+    if (!s || n < 0 || (n > 0 && (!in9 || !dir_out))) return set_err(RTB_ERR_INVALID, "bad argument");
+    if (n == 0) return RTB_OK;
+    CU(cudaSetDevice(s->device));
+    CU(s->scratch_a.reserve((size_t)n * 9 * sizeof(double)));
+    CU(s->scratch_b.reserve((size_t)n * 3 * sizeof(double)));
+    CU(cudaMemcpy(s->scratch_a.p, in9, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(launch_eval_dielectric(static_cast<const double*>(s->scratch_a.p), n, static_cast<double*>(s->scratch_b.p), 0));
+    CU(cudaMemcpy(dir_out, s->scratch_b.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return RTB_OK;
+  });
+}
+
 int rtb_philox(rtb_scene* s, const uint32_t* ctr_key, int64_t n, uint32_t* out) {
   return guarded([&]() -> int {
     if (!s || n < 0 || (n > 0 && (!ctr_key || !out))) return set_err(RTB_ERR_INVALID, "bad argument");

@@ -245,6 +245,20 @@ cudaError_t launch_accum_to_f64(const unsigned long long* d_accum, int64_t n_pix
   return cudaGetLastError();
 }
 
+// Dielectric::scatter known-answer hook: in = n x {d[3], normal[3], front, ir, u}, out = n x direction[3]
+__global__ void k_eval_dielectric(const double* __restrict__ in, long long n, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = in + 9 * i;
+  const V3 d = dielectric_direction(v3((float)a[0], (float)a[1], (float)a[2]), v3((float)a[3], (float)a[4], (float)a[5]), a[6] != 0., (float)a[7], (float)a[8]);
+  out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+}
+cudaError_t launch_eval_dielectric(const double* d_in, int64_t n, double* d_out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_eval_dielectric<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_in, n, d_out);
+  return cudaGetLastError();
+}
+
 // Random123 known-answer hook: the device's own philox4x32_10 (rtb_device.cuh) on caller-given counters / keys
 __global__ void k_philox(const uint32_t* __restrict__ ctr_key, long long n, uint32_t* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,6 +53,7 @@ cudaError_t launch_write_color(const double* d_pixels, int64_t n_values, double 
                                cudaStream_t stream);
 // fixed-point sums -> f64 radiance sums (poisoned pixels: NaN); add = 1 accumulates INTO d_pixels_rgb (Q24)
 cudaError_t launch_accum_to_f64(const unsigned long long* d_accum, int64_t n_pixels, double* d_pixels_rgb, int add, cudaStream_t stream);
+cudaError_t launch_eval_dielectric(const double* d_in, int64_t n, double* d_out, cudaStream_t stream);
 // Random123 known-answer hook: out[4*i..] = philox4x32_10(ctr[4*i..], key[2*i..]) evaluated by the device code
 cudaError_t launch_philox(const uint32_t* d_ctr_key, int64_t n, uint32_t* d_out, cudaStream_t stream);
 

@@ -1145,6 +1145,26 @@ RTB_DEV void extend(const DScene& S, const PathState& ps, Event& ev, DStats* st)
   }
 }
 
+// Dielectric::scatter  material.rs:167-191 (Q15): Schlick reflectance :156-163, reflect / refract  vec3.rs:219-229.
+// `n` is the face normal (against the ray), `u` the uniform draw (consumed only when refraction is possible).
+RTB_DEV V3 dielectric_direction(V3 d, V3 n, bool front, float ir, float u) {
+  const float ratio = front ? fast_rcp(ir) : ir;
+  const V3 ud = normalize(d);
+  const float cos_theta = fminf(dot(-ud, n), 1.f);
+  const float sin_theta = fast_sqrt(1.f - cos_theta * cos_theta);
+  bool reflect_it = ratio * sin_theta > 1.f;
+  if (!reflect_it) {
+    float r0 = fast_div(1.f - ratio, 1.f + ratio);
+    r0 = r0 * r0;
+    const float x = 1.f - cos_theta, x2 = x * x;
+    reflect_it = (r0 + (1.f - r0) * (x2 * x2 * x)) > u;
+  }
+  if (reflect_it) return ud - (2.f * dot(ud, n)) * n;
+  const V3 perp = ratio * (ud + cos_theta * n);
+  const V3 par = -fast_sqrt(fabsf(1.f - dot(perp, perp))) * n;
+  return perp + par;
+}
+
 // material response at the event; returns false when the path ends (contribution added to L)
 // LIGHTS = false compiles the light-list sampler (HittablePDF: f64 probes per light) out: the wavefront shade
 // kernel instantiates it for scenes whose light list is empty (what render_par passes, F2).
@@ -1233,25 +1253,8 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
     const V3 refl = ud - (2.f * dot(ud, n)) * n;
     dir = normalize(refl) + m.param * random_unit_vector(u.z, u.w);
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
-  } else if (m.kind == MAT_DIELECTRIC) {  // material.rs:167-191 (Q15), vec3.rs:219-229
-    const float ratio = front ? fast_rcp(m.param) : m.param;
-    const V3 ud = normalize(v3((float)r.dx, (float)r.dy, (float)r.dz));
-    const float cos_theta = fminf(dot(-ud, n), 1.f);
-    const float sin_theta = fast_sqrt(1.f - cos_theta * cos_theta);
-    bool reflect_it = ratio * sin_theta > 1.f;
-    if (!reflect_it) {
-      float r0 = fast_div(1.f - ratio, 1.f + ratio);
-      r0 = r0 * r0;
-      const float x = 1.f - cos_theta, x2 = x * x;
-      reflect_it = (r0 + (1.f - r0) * (x2 * x2 * x)) > u.x;
-    }
-    if (reflect_it) {
-      dir = ud - (2.f * dot(ud, n)) * n;
-    } else {
-      const V3 perp = ratio * (ud + cos_theta * n);
-      const V3 par = -fast_sqrt(fabsf(1.f - dot(perp, perp))) * n;
-      dir = perp + par;
-    }
+  } else if (m.kind == MAT_DIELECTRIC) {
+    dir = dielectric_direction(v3((float)r.dx, (float)r.dy, (float)r.dz), n, front, m.param, u.x);
     ps.bx *= m.color[0]; ps.by *= m.color[1]; ps.bz *= m.color[2];
   } else {
     // PdfPtr arm  src/render.rs:278-293: MixturePDF(HittablePDF(lights), material pdf)  pdf.rs:102-127

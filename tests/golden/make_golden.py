@@ -4,7 +4,9 @@
   ref_book3_150.npy / ref_mixed_pdf_150.npy
         4x4 block means (150x150x3, float32, 8-bit sRGB scale) of the reference's own shipped
         renders final_images/book3.png (cornell_box at HEAD = config c5) and
-        final_images/mixed_pdf.png (= config c2).  The oracle is pinned against these by PSNR.
+        final_images/mixed_pdf.png (= config c2), and ref_cornell_smoke_150.npy of final_images/cornell_smoke.png
+        (= config c3: deterministic geometry src/main.rs:514-601, scattering smoke = ISO 1/(4 pi), lights = empty).
+        The oracle is pinned against these by PSNR.
   oracle_<cfg>[_lights].npz
         per-pixel mean and variance of the ORACLE (reference sampler mode, f64) at reduced
         resolution and 1024 spp: the "high-spp CPU render" the GPU images are accepted against.
@@ -31,7 +33,8 @@ GOLDEN_RENDERS = {  # name: (config, variant, width, spp)
 
 def reference_pngs():
     from PIL import Image
-    for png, out in (("book3.png", "ref_book3_150.npy"), ("mixed_pdf.png", "ref_mixed_pdf_150.npy")):
+    for png, out in (("book3.png", "ref_book3_150.npy"), ("mixed_pdf.png", "ref_mixed_pdf_150.npy"),
+                     ("cornell_smoke.png", "ref_cornell_smoke_150.npy")):
         img = np.asarray(Image.open(f"/root/reference/final_images/{png}").convert("RGB")).astype(np.float64)
         assert img.shape == (600, 600, 3)
         blocks = img.reshape(150, 4, 150, 4, 3).mean(axis=(1, 3)).astype(np.float32)
