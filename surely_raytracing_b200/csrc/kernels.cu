@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DSc
   PathState ps;
   bool alive = false;
   float Lr = 0.f, Lg = 0.f, Lb = 0.f;
+  RTB_LOOP_ENTER();
   for (;;) {
     if (!alive) {
       if (s >= s_end) break;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DSc
       }
     }
   }
+  RTB_LOOP_LEAVE();
   unsigned long long* a = accum + 4ull * pixel;
   a[0] += sum_r; a[1] += sum_g; a[2] += sum_b;
   a[3] = (a[3] + (unsigned long long)(s_end - s_begin)) | poison;
@@ -140,12 +142,34 @@ __global__ void __launch_bounds__(128) k_trace_complete(const __grid_constant__ 
   hits[i] = out;
 }
 
+#if defined(RTB_TRACE_FUSED)
+// Investigation arm (tools/repro_fused.sh): traversal and hit completion in ONE kernel, the form that faulted in round 1.
+__global__ void __launch_bounds__(128) k_trace_fused(const __grid_constant__ DScene S, const RtbRay* __restrict__ rays,
+                                                     long long n, uint32_t flags, RtbHit* __restrict__ hits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RtbRay in = rays[i];
+  const Ray r = load_ray(in);
+  Hit best;
+  hit_reset(best);
+  if (flags & RTB_TRACE_BRUTE_FORCE) closest_surface_brute(S, r, in.t_min, best);
+  else if (S.n_surface_prims > 0) closest_surface<false>(S, r, in.t_min, best, nullptr);
+  RtbHit out;
+  complete_hit(S, r, best, out);
+  hits[i] = out;
+}
+#endif
+
 size_t trace_scratch_bytes(int64_t n) { return (size_t)n * sizeof(TraceHit); }
 
 cudaError_t launch_trace(const DScene& S, const RtbRay* d_rays, int64_t n, uint32_t flags, RtbHit* d_hits,
                          void* d_scratch, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 127) / 128);
+#if defined(RTB_TRACE_FUSED)
+  k_trace_fused<<<blocks, 128, 0, stream>>>(S, d_rays, n, flags, d_hits);
+  return cudaGetLastError();
+#endif
   k_trace_closest<<<blocks, 128, 0, stream>>>(S, d_rays, n, flags, static_cast<TraceHit*>(d_scratch));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -197,7 +221,9 @@ __global__ void k_eval_light_pdf(const __grid_constant__ DScene S, const double*
   probe.dx = od[6 * i + 3]; probe.dy = od[6 * i + 4]; probe.dz = od[6 * i + 5];
   probe.time = 0.;
   double sum = 0.;
+  RTB_LOOP_ENTER();
   for (int k = 0; k < S.n_lights; k++) sum += light_pdf_one(S.lights[k], probe);
+  RTB_LOOP_LEAVE();
   pdf[i] = sum * (1. / (double)S.n_lights);
 }
 cudaError_t launch_eval_light_pdf(const DScene& S, const double* d_od, int64_t n, double* d_pdf, cudaStream_t stream) {

@@ -57,6 +57,18 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {  // PRM
 
 namespace rtb {
 
+// Lanes leave a divergent loop one by one.  ptxas keeps loop invariants in UNIFORM registers -- one copy per warp --
+// and lets the early leavers run on into code that reuses those registers (BREAK + a branch past the BSYNC): in round 1
+// that sent the lanes still traversing to a wild address (DESIGN.md "The -O3 fault"; tools/sass_lint.py).  Every
+// divergent loop of the path therefore ends in an explicit reconvergence of the lanes that entered it together.
+#if defined(__CUDACC__)
+#define RTB_LOOP_ENTER() const unsigned rtb_loop_mask__ = __activemask()
+#define RTB_LOOP_LEAVE() __syncwarp(rtb_loop_mask__)
+#else
+#define RTB_LOOP_ENTER() ((void)0)
+#define RTB_LOOP_LEAVE() ((void)0)
+#endif
+
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr double PI_D = 3.14159265358979323846;
 constexpr double RTB_INF = __builtin_huge_val();  // +inf
@@ -404,6 +416,7 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
   int stack[BVH_STACK];
   int sp = 0;
   int node = 0;
+  RTB_LOOP_ENTER();
   for (;;) {
     if (node >= 0) {
       if (STATS) st->node_visits++;
@@ -432,6 +445,7 @@ RTB_DEV void closest_surface(const DScene& S, const Ray& r, double tmin, Hit& be
     if (sp == 0) break;
     node = stack[--sp];
   }
+  RTB_LOOP_LEAVE();
 }
 
 // linear scan over all surface primitives (RTB_TRACE_BRUTE_FORCE: validates the BVH cull)
@@ -671,6 +685,8 @@ RTB_DEV bool closest_candidates(const DScene& S, const Ray& r, float scene_mag, 
   cands_reset(C);
   int stack[BVH_STACK];
   int sp = 0, node = 0;
+  RTB_LOOP_ENTER();
+  bool complete = true;
   for (;;) {
     if (node >= 0) {
       if (STATS) st->node_visits++;
@@ -692,12 +708,13 @@ RTB_DEV bool closest_candidates(const DScene& S, const Ray& r, float scene_mag, 
     } else {
       const int count = prefilter_leaf<true>(S, node, pr, tmin_lo, tmin_hi, C);
       if (STATS) st->prim_tests += (unsigned long long)count;
-      if (C.c0 == CAND_OVERFLOW) return false;
+      if (C.c0 == CAND_OVERFLOW) { complete = false; break; }
     }
     if (sp == 0) break;
     node = stack[--sp];
   }
-  return true;
+  RTB_LOOP_LEAVE();
+  return complete;
 }
 
 // ------------------------------------------------------------------------------------------------

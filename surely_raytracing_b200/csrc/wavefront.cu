@@ -808,12 +808,14 @@ __global__ void __launch_bounds__(128) k_wf_finish(const __grid_constant__ DScen
   DStats st = {};
   float Lr = 0.f, Lg = 0.f, Lb = 0.f;
   bool alive = true;
+  RTB_LOOP_ENTER();
   while (alive) {
     Event ev;
     if (STATS) st.segments++;
     extend<STATS>(S, ps, ev, &st);
     alive = shade(S, ps, ev, Lr, Lg, Lb, &st, STATS);  // (scattered directions are fp32-valued, as in the queues)
   }
+  RTB_LOOP_LEAVE();
   wf_accumulate(S, accum, p.pixel, Lr, Lg, Lb, st, STATS);
   if (STATS) {
     atomicAdd(&stats->segments, st.segments);

@@ -118,3 +118,17 @@ def test_every_config_flattens_on_the_host():
             assert (i.n_surface_prims, i.n_boundary_prims, i.n_media, i.n_lights) == exp, cfg
         else:
             assert 400 < i.n_surface_prims <= 488
+
+
+def test_no_kernel_carries_a_uniform_register_across_an_escaping_loop_exit():
+    """tools/sass_lint.py over the shipped library.  Round 1's "illegal memory access" was ptxas keeping a loop-invariant
+    address in a (per-warp) uniform register across the divergent traversal loop and reusing that register in code the
+    early leavers of the loop could reach (tests/golden/sass_fault_r01.txt is that kernel's listing: the lint must flag
+    it); every divergent loop now ends in an explicit reconvergence, and no shipped kernel may show the pattern."""
+    import subprocess
+    import sys
+    lint = str(ROOT / "tools" / "sass_lint.py")
+    bad = subprocess.run([sys.executable, lint, str(ROOT / "tests" / "golden" / "sass_fault_r01.txt")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "UR5" in bad.stdout, bad.stdout
+    good = subprocess.run([sys.executable, lint, str(capi.LIB_PATH)], capture_output=True, text=True)
+    assert good.returncode == 0 and good.stdout.count("ok ") >= 40, good.stdout[-2000:]
