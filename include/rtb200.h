@@ -142,6 +142,10 @@ typedef struct RtbCamera {
  * `suns` is accepted and ignored (Q23).  This flag switches the term back on: a miss adds, for every sun,
  * Sun::_hit (src/object.rs:232-239): albedo if dot(unit(d), direction) > 1 - angular_diameter/180. */
 #define RTB_FLAG_SUN_LIGHT 0x100u
+/* Opt-in Russian roulette (NOT in the reference, whose only terminations are max_depth, a miss and an emitter): from the
+ * 4th bounce on a path survives with probability q = clamp(max(throughput), 0.05, 1) and its throughput is divided by q.
+ * Unbiased, fewer segments per path, more variance per path; the default stays the reference's estimator. */
+#define RTB_FLAG_RUSSIAN_ROULETTE 0x200u
 
 /* Sun::new (reference src/object.rs:223-231) */
 typedef struct RtbSun {
@@ -298,6 +302,13 @@ int rtb_accum_to_pixels(rtb_scene* scene, const void* d_accum_u64x4, double* pix
  * on n_devices (bit-identical).  stats (may be NULL): sums over devices, device_ms = the slowest device. */
 int rtb_render_multi(const RtbSceneDesc* desc, int n_devices, const int* devices, const RtbRenderParams* params,
                      double* pixels_rgb, RtbStats* stats);
+
+/* On-disk checkpoints of a progressive render: the accumulation buffer (fixed-point sums + strata counts) of `scene`'s
+ * image size, written to / read from `path` (64-byte header: magic, abi, width, height, seed, flags; then w*h*4 u64).
+ * Because the sums are exact integers, "render [0,k), save, ... load, render [k,n)" leaves the very bits of one
+ * uninterrupted render of [0,n).  load OVERWRITES d_accum_u64x4 and fails if the file belongs to another image size or seed. */
+int rtb_checkpoint_save(rtb_scene* scene, const void* d_accum_u64x4, const char* path);
+int rtb_checkpoint_load(rtb_scene* scene, void* d_accum_u64x4, const char* path);
 
 int rtb_scene_set_option(rtb_scene* scene, int option /* RtbOption */, int64_t value);
 /* frees the idle blocks of the process-wide buffer cache (queues, staging); returns the bytes released */

@@ -1,11 +1,17 @@
-//! `extern "C"` mirror of include/rtb200.h (ABI version 1). Field order and types must match the
+//! `extern "C"` mirror of include/rtb200.h (ABI version 2). Field order and types must match the
 //! header exactly; tests/test_abi.py pins the struct sizes on the C side.
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RTB_ABI_VERSION: i32 = 1;
+pub const RTB_ABI_VERSION: i32 = 2;
 pub const RTB_FLAG_ISO_PDF_ZERO: u32 = 1;
 pub const RTB_FLAG_PROPAGATE_NAN: u32 = 2;
+pub const RTB_FLAG_BVH4: u32 = 0x10;
+pub const RTB_FLAG_QNODES: u32 = 0x20;
+pub const RTB_FLAG_BVH_LEAF4: u32 = 0x40;
+pub const RTB_FLAG_NO_BOX_SCAN: u32 = 0x80;
+/// switches the sun term HEAD comments out (src/render.rs:300-308) back on
+pub const RTB_FLAG_SUN_LIGHT: u32 = 0x100;
 
 pub const OBJ_SPHERE: i32 = 0;
 pub const OBJ_QUAD: i32 = 1;
@@ -91,6 +97,14 @@ pub struct RtbCamera {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RtbSun {
+    pub direction: [f64; 3],
+    pub albedo: [f64; 3],
+    pub angular_diameter: f64,
+}
+
+#[repr(C)]
 pub struct RtbSceneDesc {
     pub abi_version: i32,
     pub flags: u32,
@@ -111,6 +125,9 @@ pub struct RtbSceneDesc {
     pub perlins: *const RtbPerlin,
     pub n_perlins: i32,
     pub camera: RtbCamera,
+    pub suns: *const RtbSun,
+    pub n_suns: i32,
+    pub reserved: i32,
 }
 
 #[repr(C)]
@@ -150,6 +167,9 @@ pub struct RtbStats {
     pub nonfinite_samples: u64,
     pub kernel_launches: u64,
     pub device_ms: f64,
+    pub exact_tests: u64,
+    pub overflow_rays: u64,
+    pub stage_ms: [f64; 3],
 }
 
 #[repr(C)]
@@ -165,6 +185,16 @@ extern "C" {
     pub fn rtb_scene_destroy(scene: *mut rtb_scene);
     pub fn rtb_scene_info(scene: *const rtb_scene, info: *mut RtbSceneInfo) -> c_int;
     pub fn rtb_render(scene: *mut rtb_scene, params: *const RtbRenderParams, pixels_rgb: *mut f64, stats: *mut RtbStats) -> c_int;
-    pub fn rtb_render_device(scene: *mut rtb_scene, params: *const RtbRenderParams, d_accum_rgba: *mut c_void, cuda_stream: *mut c_void) -> c_int;
+    /// d_accum: w*h x 4 u64 {r, g, b, count}, 2^-32 fixed-point sums (order-independent: bit-reproducible, split-invariant)
+    pub fn rtb_render_device(scene: *mut rtb_scene, params: *const RtbRenderParams, d_accum_u64x4: *mut c_void, cuda_stream: *mut c_void) -> c_int;
+    pub fn rtb_render_stats(scene: *mut rtb_scene, stats: *mut RtbStats) -> c_int;
+    pub fn rtb_accum_to_pixels(scene: *mut rtb_scene, d_accum_u64x4: *const c_void, pixels_rgb: *mut f64) -> c_int;
+    /// the reference seam on the GPUs of one box: threads + streams per GPU, one NCCL int64 sum-reduce, one D2H
+    pub fn rtb_render_multi(desc: *const RtbSceneDesc, n_devices: c_int, devices: *const c_int, params: *const RtbRenderParams,
+                            pixels_rgb: *mut f64, stats: *mut RtbStats) -> c_int;
+    pub fn rtb_scene_set_option(scene: *mut rtb_scene, option: c_int, value: i64) -> c_int;
+    pub fn rtb_trim_cache() -> i64;
+    /// auto_expose (src/render.rs:325-339) in the reference's own sequential order
+    pub fn rtb_auto_expose(pixels_rgb: *const f64, n_pixels: i64, spp: f64, exposure_out: *mut f64) -> c_int;
     pub fn rtb_write_color(scene: *mut rtb_scene, pixels_rgb: *const f64, n_pixels: i64, spp: f64, exposure: f64, rgb8_out: *mut u8) -> c_int;
 }

@@ -34,39 +34,54 @@ pub fn render_par(cam: &Camera, world: &HittableList, pixels: &mut Vec<Color>, s
     render_par_lights(cam, world, pixels, suns, Arc::new(Object::List(Arc::new(HittableList::new()))))
 }
 
-/// reference src/render.rs:144-216.  Same signature; the rayon loop is one call into librtb200.so.
-/// Panics on error, like the reference does (`expect`/`panic!`).
-pub fn render_par_lights(cam: &Camera, world: &HittableList, pixels: &mut Vec<Color>, _suns: &Vec<Sun>, lights: Arc<Object>) {
+/// reference src/render.rs:144-216.  Same signature; the rayon loop is one call into librtb200.so -- rtb_render on one
+/// GPU, rtb_render_multi (one thread + stream per GPU, one NCCL int64 sum-reduce, one read-back) when the job keeps more
+/// than one of the box's GPUs busy (>= 128 M paths each; RTB_GPUS overrides).  Panics on error, like the reference does.
+pub fn render_par_lights(cam: &Camera, world: &HittableList, pixels: &mut Vec<Color>, suns: &Vec<Sun>, lights: Arc<Object>) {
     println!("P3\n{} {}\n255", cam.image_width, cam.image_height());
-    let flat = FlatScene::new(cam, world, &lights);
+    let mut flat = FlatScene::new(cam, world, &lights);
+    flat.set_suns(suns);
     let desc = flat.desc();
-    let mut scene: *mut ffi::rtb_scene = std::ptr::null_mut();
-    let rc = unsafe { ffi::rtb_scene_create(&desc, 0, &mut scene) };
-    if rc != 0 {
-        panic!("rtb_scene_create: {}", last_error());
-    }
-    let mut info = ffi::RtbSceneInfo::default();
-    unsafe { ffi::rtb_scene_info(scene, &mut info) };
-    assert_eq!(pixels.len(), (info.image_width * info.image_height) as usize, "use init_pixels");
-    let params = ffi::RtbRenderParams { sample_begin: 0, sample_end: info.spp_used as i64, pipeline: 0, collect_stats: 0 };
+    let root = (cam.samples_per_pixel as f64).sqrt() as i64;
+    let spp_used = root * root; // nearest_square, src/render.rs:38-41, 108
+    assert_eq!(pixels.len(), (cam.image_height() * cam.image_width) as usize, "use init_pixels");
+    let visible = unsafe { ffi::rtb_device_count() } as i64;
+    let wanted = std::env::var("RTB_GPUS").ok().and_then(|v| v.parse::<i64>().ok())
+        .unwrap_or((spp_used * pixels.len() as i64) / (128 << 20));
+    let n_dev = wanted.clamp(1, visible.max(1)) as i32;
+    let params = ffi::RtbRenderParams { sample_begin: 0, sample_end: spp_used, pipeline: 0, collect_stats: 0 };
     // Color is #[repr(C)] {x, y, z: f64}: the pixel vector is the f64 rgb-sum buffer the ABI wants
-    let rc = unsafe { ffi::rtb_render(scene, &params, pixels.as_mut_ptr() as *mut f64, std::ptr::null_mut()) };
-    if rc != 0 {
-        let msg = last_error();
+    let px = pixels.as_mut_ptr() as *mut f64;
+    let rc = if n_dev > 1 {
+        unsafe { ffi::rtb_render_multi(&desc, n_dev, std::ptr::null(), &params, px, std::ptr::null_mut()) }
+    } else {
+        let mut scene: *mut ffi::rtb_scene = std::ptr::null_mut();
+        let rc = unsafe { ffi::rtb_scene_create(&desc, 0, &mut scene) };
+        if rc != 0 {
+            panic!("rtb_scene_create: {}", last_error());
+        }
+        let rc = unsafe { ffi::rtb_render(scene, &params, px, std::ptr::null_mut()) };
         unsafe { ffi::rtb_scene_destroy(scene) };
-        panic!("rtb_render: {}", msg);
+        rc
+    };
+    if rc != 0 {
+        panic!("render: {}", last_error());
     }
     eprintln!("\rWriting...            ");
+    // src/render.rs:201-213: `if cam.auto_exposure { Some(auto_expose(cam, pixels)) } else { None }`, then write_color per pixel
+    let mut exposure = 0.0f64; // <= 0: None
+    if cam.auto_exposure && unsafe { ffi::rtb_auto_expose(px, pixels.len() as i64, spp_used as f64, &mut exposure) } != 0 {
+        panic!("rtb_auto_expose: {}", last_error());
+    }
     let mut rgb8 = vec![0u8; pixels.len() * 3];
-    let rc = unsafe { ffi::rtb_write_color(scene, pixels.as_ptr() as *const f64, pixels.len() as i64, info.spp_used as f64, 0.0, rgb8.as_mut_ptr()) };
+    let rc = unsafe { ffi::rtb_write_color(std::ptr::null_mut(), px, pixels.len() as i64, spp_used as f64, exposure, rgb8.as_mut_ptr()) };
     if rc != 0 {
         panic!("rtb_write_color: {}", last_error());
     }
     let mut text = String::with_capacity(pixels.len() * 12);
-    for px in rgb8.chunks(3) {
-        text.push_str(&format!("{} {} {}\n", px[0], px[1], px[2]));
+    for p in rgb8.chunks(3) {
+        text.push_str(&format!("{} {} {}\n", p[0], p[1], p[2]));
     }
     print!("{}", text);
-    unsafe { ffi::rtb_scene_destroy(scene) };
     eprintln!("\rDone!                           ");
 }

@@ -1,6 +1,6 @@
 //! Scene-construction API with the reference's names and signatures, plus `flatten`.
 use crate::ffi::*;
-use crate::host_rng::{random_int, random_range};
+use crate::host_rng::{random_double, random_int, random_range};
 use std::sync::Arc;
 
 #[repr(C)]
@@ -20,7 +20,8 @@ impl Vec3 {
     pub fn y(&self) -> f64 { self.y }
     pub fn z(&self) -> f64 { self.z }
     fn arr(&self) -> [f64; 3] { [self.x, self.y, self.z] }
-    fn length(&self) -> f64 { (self.x * self.x + self.y * self.y + self.z * self.z).sqrt() }
+    pub fn length_squared(&self) -> f64 { self.x * self.x + self.y * self.y + self.z * self.z }
+    pub fn length(&self) -> f64 { self.length_squared().sqrt() }
 }
 impl std::ops::Add for Vec3 { type Output = Vec3; fn add(self, o: Vec3) -> Vec3 { Vec3::new(self.x + o.x, self.y + o.y, self.z + o.z) } }
 impl std::ops::Sub for Vec3 { type Output = Vec3; fn sub(self, o: Vec3) -> Vec3 { Vec3::new(self.x - o.x, self.y - o.y, self.z - o.z) } }
@@ -28,7 +29,14 @@ impl std::ops::Neg for Vec3 { type Output = Vec3; fn neg(self) -> Vec3 { Vec3::n
 impl std::ops::Mul<Vec3> for f64 { type Output = Vec3; fn mul(self, v: Vec3) -> Vec3 { Vec3::new(self * v.x, self * v.y, self * v.z) } }
 impl std::ops::Mul<Vec3> for Vec3 { type Output = Vec3; fn mul(self, v: Vec3) -> Vec3 { Vec3::new(self.x * v.x, self.y * v.y, self.z * v.z) } }
 impl std::ops::Div<f64> for Vec3 { type Output = Vec3; fn div(self, t: f64) -> Vec3 { Vec3::new(self.x / t, self.y / t, self.z / t) } }
+impl std::ops::Mul<f64> for Vec3 { type Output = Vec3; fn mul(self, t: f64) -> Vec3 { t * self } }              // vec3.rs:113-119 (`Color::new(..) * 10.`, main.rs:86)
+impl std::ops::AddAssign for Vec3 { fn add_assign(&mut self, o: Vec3) { *self = *self + o; } }                     // vec3.rs:74-80
+impl std::ops::MulAssign<f64> for Vec3 { fn mul_assign(&mut self, t: f64) { *self = t * *self; } }                 // vec3.rs:121-127
+impl std::ops::DivAssign<f64> for Vec3 { fn div_assign(&mut self, t: f64) { *self = *self / t; } }                 // vec3.rs:153-157
+pub fn dot(u: &Vec3, v: &Vec3) -> f64 { u.x * v.x + u.y * v.y + u.z * v.z }                                        // vec3.rs:167-169
+pub fn cross(u: &Vec3, v: &Vec3) -> Vec3 { Vec3::new(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x) }  // vec3.rs:171-177
 pub fn unit_vector(v: &Vec3) -> Vec3 { *v / v.length() }
+pub fn random_vec3() -> Vec3 { Vec3::new(random_double(), random_double(), random_double()) }                      // vec3.rs:193-195
 pub fn random_vec3_range(min: f64, max: f64) -> Vec3 { Vec3::new(random_range(min, max), random_range(min, max), random_range(min, max)) }
 
 // ---- textures -----------------------------------------------------------------------------------
@@ -51,6 +59,34 @@ impl ImageTexture {
     /// RGB8, top row first (what `image::open(..).to_rgb8()` yields). A crate user with the `image`
     /// dependency decodes the file and passes the bytes; the library never touches the file system.
     pub fn from_rgb8(width: i32, height: i32, rgb: Vec<u8>) -> Texture { Texture::Image { width, height, rgb: Arc::new(rgb) } }
+
+    /// reference src/texture.rs:89 + src/rt_image.rs:13-27: decode `filename` to RGB8.  With the `image` feature the
+    /// file goes through the same `image` crate call the reference makes (`image::open(..).to_rgb8()`); without it only
+    /// binary PPM (P6, maxval 255) is read.  Panics like the reference when the file cannot be opened.
+    pub fn new(filename: &str) -> Texture {
+        #[cfg(feature = "image")]
+        {
+            let img = image::open(filename).expect("Could not open image.").to_rgb8();
+            let (w, h) = (img.width() as i32, img.height() as i32);
+            return Self::from_rgb8(w, h, img.into_raw());
+        }
+        #[cfg(not(feature = "image"))]
+        {
+            let bytes = std::fs::read(filename).expect("Could not open image.");
+            let mut fields = Vec::new();
+            let mut pos = 0usize;
+            while fields.len() < 4 {
+                while pos < bytes.len() && bytes[pos].is_ascii_whitespace() { pos += 1; }
+                let start = pos;
+                while pos < bytes.len() && !bytes[pos].is_ascii_whitespace() { pos += 1; }
+                fields.push(String::from_utf8_lossy(&bytes[start..pos]).into_owned());
+            }
+            pos += 1;
+            let (w, h): (usize, usize) = (fields[1].parse().expect("Could not open image."), fields[2].parse().expect("Could not open image."));
+            assert!(fields[0] == "P6" && fields[3] == "255" && bytes.len() >= pos + 3 * w * h, "Could not open image.");
+            Self::from_rgb8(w as i32, h as i32, bytes[pos..pos + 3 * w * h].to_vec())
+        }
+    }
 }
 pub struct NoiseTexture;
 impl NoiseTexture {
@@ -120,8 +156,13 @@ pub struct RotateY;
 impl RotateY { pub fn new(p: Arc<Object>, angle: f64) -> Object { Object::RotateY { object: p, angle } } }
 pub struct ConstantMedium;
 impl ConstantMedium { pub fn new(boundary: Arc<Object>, density: f64, c: Color) -> Object { Object::Volume { boundary, density, phase: Isotropic::new(c) } } }
-pub struct Sun;
-impl Sun { pub fn new(_direction: Vec3, _albedo: Color, _angular_diameter: f64) -> Sun { Sun } }
+/// reference src/object.rs:216-241.  Accepted and ignored by the integrator at HEAD (the sun term of ray_color is
+/// commented out, src/render.rs:300-308); the records still reach the library, which adds the term back under
+/// RTB_FLAG_SUN_LIGHT.
+pub struct Sun { pub direction: Vec3, pub albedo: Color, pub angular_diameter: f64 }
+impl Sun {
+    pub fn new(direction: Vec3, albedo: Color, angular_diameter: f64) -> Sun { Sun { direction: unit_vector(&direction), albedo, angular_diameter } }
+}
 
 pub struct HittableList { pub objects: Vec<Object> }
 impl HittableList {
@@ -184,6 +225,9 @@ pub struct FlatScene {
     images: Vec<RtbImage>,
     image_bytes: Vec<Arc<Vec<u8>>>,
     perlins: Vec<RtbPerlin>,
+    suns: Vec<RtbSun>,
+    tex_seen: Vec<(*const Texture, i32)>,     // textures are interned by Arc pointer, materials by value:
+    mat_seen: Vec<(RtbMaterial, i32)>,        // final_scene's 1000 spheres share ONE white Lambertian record
     world: i32,
     camera: Option<RtbCamera>,
     pub flags: u32,
@@ -199,13 +243,26 @@ impl FlatScene {
             vup: cam.vup.arr(), defocus_angle: cam.defocus_angle, focus_dist: cam.focus_dist, background: cam.background.arr(),
         });
         f.world = f.emit_list(&world.objects, OBJ_LIST);
-        if let Object::List(l) = &**lights {
-            for o in l.objects.iter() {
-                let id = f.emit(o);
+        // `lights: Arc<Object>` (src/render.rs:149): pdf_value / random dispatch on ANY object (src/object.rs:53-69) --
+        // a list contributes its members, a bare Quad or Sphere is a one-element list, any other kind falls to the
+        // Hittable defaults (pdf 0, direction (1,0,0): src/hittable.rs:46-52), which the library reproduces
+        match &**lights {
+            Object::List(l) | Object::Node(l) => {
+                for o in l.objects.iter() {
+                    let id = f.emit(o);
+                    f.lights.push(id);
+                }
+            }
+            other => {
+                let id = f.emit(other);
                 f.lights.push(id);
             }
         }
         f
+    }
+
+    pub fn set_suns(&mut self, suns: &[Sun]) {
+        self.suns = suns.iter().map(|s| RtbSun { direction: s.direction.arr(), albedo: s.albedo.arr(), angular_diameter: s.angular_diameter }).collect();
     }
 
     pub fn desc(&self) -> RtbSceneDesc {
@@ -219,10 +276,18 @@ impl FlatScene {
             images: self.images.as_ptr(), n_images: self.images.len() as i32,
             perlins: self.perlins.as_ptr(), n_perlins: self.perlins.len() as i32,
             camera: self.camera.unwrap(),
+            suns: self.suns.as_ptr(), n_suns: self.suns.len() as i32, reserved: 0,
         }
     }
 
     fn emit_texture(&mut self, t: &Texture) -> i32 {
+        if let Some((_, id)) = self.tex_seen.iter().find(|(p, _)| std::ptr::eq(*p, t)) { return *id; }
+        let id = self.emit_texture_new(t);
+        self.tex_seen.push((t as *const Texture, id));
+        id
+    }
+
+    fn emit_texture_new(&mut self, t: &Texture) -> i32 {
         let mut r = RtbTexture { kind: TEX_SOLID, a: -1, b: -1, reserved: 0, color: [0.; 3], scale: 1. };
         match t {
             Texture::Solid(c) => { r.color = c.arr(); }
@@ -247,8 +312,13 @@ impl FlatScene {
             Material::DiffuseLight(t) => RtbMaterial { kind: MAT_DIFFUSE_LIGHT, texture: self.emit_texture(t), color: [0.; 3], param: 0. },
             Material::Isotropic(t) => RtbMaterial { kind: MAT_ISOTROPIC, texture: self.emit_texture(t), color: [0.; 3], param: 0. },
         };
+        let same = |a: &RtbMaterial, b: &RtbMaterial| a.kind == b.kind && a.texture == b.texture && a.param.to_bits() == b.param.to_bits()
+            && a.color.iter().zip(b.color.iter()).all(|(x, y)| x.to_bits() == y.to_bits());
+        if let Some((_, id)) = self.mat_seen.iter().find(|(m2, _)| same(m2, &r)) { return *id; }
         self.materials.push(r);
-        self.materials.len() as i32 - 1
+        let id = self.materials.len() as i32 - 1;
+        self.mat_seen.push((r, id));
+        id
     }
 
     fn emit_list(&mut self, objs: &[Object], kind: i32) -> i32 {

@@ -60,6 +60,12 @@ class Scene:
         capi.check(self._lib, self._lib.rtb_eval_dielectric(self._h, _ptr(a), len(a), _ptr(out)), "rtb_eval_dielectric")
         return out
 
+    def checkpoint_save(self, d_accum_ptr: int, path: str):
+        capi.check(self._lib, self._lib.rtb_checkpoint_save(self._h, C.c_void_p(d_accum_ptr), str(path).encode()), "rtb_checkpoint_save")
+
+    def checkpoint_load(self, d_accum_ptr: int, path: str):
+        capi.check(self._lib, self._lib.rtb_checkpoint_load(self._h, C.c_void_p(d_accum_ptr), str(path).encode()), "rtb_checkpoint_load")
+
     def philox(self, ctr_key: np.ndarray) -> np.ndarray:
         """the device's Philox4x32-10 on n x {c0,c1,c2,c3,k0,k1} (Random123 known-answer hook)"""
         ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)

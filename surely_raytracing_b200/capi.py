@@ -19,6 +19,7 @@ RTB_ABI_VERSION = 2
 RTB_FLAG_ISO_PDF_ZERO = 1
 RTB_FLAG_PROPAGATE_NAN = 2
 RTB_FLAG_BVH4, RTB_FLAG_QNODES, RTB_FLAG_BVH_LEAF4, RTB_FLAG_NO_BOX_SCAN, RTB_FLAG_SUN_LIGHT = 0x10, 0x20, 0x40, 0x80, 0x100
+RTB_FLAG_RUSSIAN_ROULETTE = 0x200
 RTB_TRACE_BRUTE_FORCE, RTB_TRACE_WAVEFRONT, RTB_TRACE_SECONDARY = 1, 2, 4
 (OPT_WF_CAPACITY, OPT_EXACT_LEAVES, OPT_SMEM_TOP, OPT_NO_DEFER_RARE, OPT_EXTEND_BLOCKS, OPT_FINISH_BELOW, OPT_PROFILE,
  OPT_MEGA_BELOW) = range(1, 9)
@@ -119,7 +120,7 @@ EXPORTS = ["rtb_version", "rtb_device_count", "rtb_last_error", "rtb_scene_creat
            "rtb_scene_info", "rtb_render", "rtb_render_device", "rtb_render_stats", "rtb_trace",
            "rtb_camera_rays", "rtb_medium_interval", "rtb_eval_texture", "rtb_eval_light_pdf",
            "rtb_write_color", "rtb_accum_to_pixels", "rtb_render_multi", "rtb_scene_set_option", "rtb_trim_cache",
-           "rtb_auto_expose", "rtb_philox", "rtb_eval_dielectric"]
+           "rtb_auto_expose", "rtb_philox", "rtb_eval_dielectric", "rtb_checkpoint_save", "rtb_checkpoint_load"]
 
 
 class RtbError(RuntimeError):
@@ -163,6 +164,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.rtb_auto_expose.argtypes = [vp, i64, C.c_double, C.POINTER(C.c_double)]
     lib.rtb_philox.argtypes = [vp, vp, i64, vp]
     lib.rtb_eval_dielectric.argtypes = [vp, vp, i64, vp]
+    lib.rtb_checkpoint_save.argtypes = [vp, vp, C.c_char_p]
+    lib.rtb_checkpoint_load.argtypes = [vp, vp, C.c_char_p]
     if path is None:
         _lib = lib
     return lib

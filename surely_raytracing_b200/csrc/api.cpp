@@ -483,6 +483,56 @@ int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* info) {
   return RTB_OK;
 }
 
+namespace {
+struct CheckpointHeader {  // 64 bytes
+  char magic[8];           // "RTB200CK"
+  int32_t abi, width, height, reserved;
+  uint64_t seed;
+  uint32_t flags, pad;
+  uint64_t spare[3];
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header is 64 bytes");
+}  // namespace
+
+int rtb_checkpoint_save(rtb_scene* s, const void* d_accum, const char* path) {
+  return guarded([&]() -> int {
+    if (!s || !d_accum || !path) return set_err(RTB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaDeviceSynchronize());
+    const size_t n = (size_t)s->host->cam.width * s->host->cam.height * 4;
+    std::vector<unsigned long long> h(n);
+    CU(cudaMemcpy(h.data(), d_accum, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CheckpointHeader hd{};
+    std::memcpy(hd.magic, "RTB200CK", 8);
+    hd.abi = RTB_ABI_VERSION; hd.width = s->host->cam.width; hd.height = s->host->cam.height;
+    hd.seed = s->host->seed; hd.flags = s->host->flags;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return set_err(RTB_ERR_INVALID, std::string("cannot open ") + path);
+    const bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1 && std::fwrite(h.data(), sizeof(unsigned long long), n, f) == n;
+    if (std::fclose(f) != 0 || !ok) return set_err(RTB_ERR_INVALID, std::string("short write to ") + path);
+    return RTB_OK;
+  });
+}
+
+int rtb_checkpoint_load(rtb_scene* s, void* d_accum, const char* path) {
+  return guarded([&]() -> int {
+    if (!s || !d_accum || !path) return set_err(RTB_ERR_INVALID, "null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return set_err(RTB_ERR_INVALID, std::string("cannot open ") + path);
+    CheckpointHeader hd{};
+    const size_t n = (size_t)s->host->cam.width * s->host->cam.height * 4;
+    std::vector<unsigned long long> h(n);
+    const bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 && std::fread(h.data(), sizeof(unsigned long long), n, f) == n;
+    std::fclose(f);
+    if (!ok || std::memcmp(hd.magic, "RTB200CK", 8) != 0) return set_err(RTB_ERR_INVALID, "not a checkpoint of this image size");
+    if (hd.abi != RTB_ABI_VERSION || hd.width != s->host->cam.width || hd.height != s->host->cam.height || hd.seed != s->host->seed)
+      return set_err(RTB_ERR_INVALID, "checkpoint belongs to another image (size, seed or ABI differ)");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpy(d_accum, h.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    return RTB_OK;
+  });
+}
+
 int rtb_scene_set_option(rtb_scene* s, int option, int64_t value) {
   if (!s) return set_err(RTB_ERR_INVALID, "null argument");
   switch (option) {

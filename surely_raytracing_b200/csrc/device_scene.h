@@ -123,12 +123,16 @@ struct DTexture {
 struct DMedium {
   int first_prim, n_prims;  // boundary primitives (in `prims`, after the surfaces), DFS order
   int material;
-  int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere; bit 9: quads only
+  int cls_fast;  // bits 0..3: shading class of the phase function; bit 8: the boundary is one static sphere; bit 9: quads only; bit 10: an oriented box (obb_*)
   double neg_inv_density;
   float lo[3], hi[3];       // padded fp32 box of the boundary (line cull)
   float diag;               // diagonal of that box: no chord of the boundary is longer
   float pad;
   float sphere[4];          // boundary = one static sphere (cls_fast bit 8): centre, and r^2 shrunk by 1e-3 relative (inside test)
+  // boundary = the six quads of a make_box under any Translate / RotateY chain (cls_fast bit 10): its oriented box.
+  // fp32 and conservative: half_out is inflated, half_in deflated by 1e-5 x scene magnitude (device: medium_obb)
+  float obb_c[3], obb_ax[3][3], obb_half_out[3], obb_half_in[3];
+  float pad2[2];
 };
 
 struct alignas(32) DLight {

@@ -740,6 +740,61 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
       for (const Baked& b : B.boundaries[mi]) all_quads = all_quads && b.kind == PRIM_QUAD;
       if (all_quads && !(d.flags & RTB_FLAG_NO_BOX_SCAN)) m.cls_fast |= 0x200;
     }
+    if ((m.cls_fast & 0x200) && m.n_prims == 6) {
+      // the six quads of a make_box (src/object.rs:509-560) after baking: an oriented box?  Axes from the first quad,
+      // every quad's normal along one axis, its corners on one face and spanning the other two extents.
+      const std::vector<Baked>& q6 = B.boundaries[mi];
+      auto vec = [](const double* p) { return D3{p[0], p[1], p[2]}; };
+      const D3 u0 = vec(q6[0].payload + 7), v0 = vec(q6[0].payload + 10);
+      const D3 ax[3] = {unit(u0), unit(v0), unit(cross(u0, v0))};
+      const double scale = std::max(length(u0), length(v0));
+      bool ok = std::fabs(dot(ax[0], ax[1])) < 1e-9;
+      double lo3[3] = {kInf, kInf, kInf}, hi3[3] = {-kInf, -kInf, -kInf};
+      for (const Baked& b : q6) {
+        const D3 q = vec(b.payload + 4), u = vec(b.payload + 7), v = vec(b.payload + 10);
+        for (const D3& c : {q, q + u, q + v, q + u + v})
+          for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], dot(c, ax[k])); hi3[k] = std::max(hi3[k], dot(c, ax[k])); }
+      }
+      int faces = 0;
+      for (const Baked& b : q6) {
+        const D3 n = vec(b.payload), q = vec(b.payload + 4), u = vec(b.payload + 7), v = vec(b.payload + 10);
+        int k = -1;
+        for (int a = 0; a < 3; a++)
+          if (std::fabs(std::fabs(dot(n, ax[a])) - 1.) < 1e-9) k = a;
+        if (k < 0) { ok = false; break; }
+        const double tol = 1e-9 * std::max(scale, 1.);
+        double cmin[3] = {kInf, kInf, kInf}, cmax[3] = {-kInf, -kInf, -kInf};
+        for (const D3& c : {q, q + u, q + v, q + u + v})
+          for (int a = 0; a < 3; a++) { cmin[a] = std::min(cmin[a], dot(c, ax[a])); cmax[a] = std::max(cmax[a], dot(c, ax[a])); }
+        const bool on_lo = std::fabs(cmin[k] - lo3[k]) < tol && std::fabs(cmax[k] - lo3[k]) < tol;
+        const bool on_hi = std::fabs(cmin[k] - hi3[k]) < tol && std::fabs(cmax[k] - hi3[k]) < tol;
+        if (!(on_lo || on_hi)) { ok = false; break; }
+        for (int a = 0; a < 3; a++)
+          if (a != k && (std::fabs(cmin[a] - lo3[a]) > tol || std::fabs(cmax[a] - hi3[a]) > tol)) ok = false;
+        faces |= 1 << (2 * k + (on_hi ? 1 : 0));
+      }
+      if (ok && faces == 63) {
+        m.cls_fast |= 0x400;
+        const double margin = 1e-5 * M;  // fp32 evaluation of the local coordinates at scene magnitude M errs by ~1e-6 M
+        for (int k = 0; k < 3; k++) {
+          const double centre_k = 0.5 * (lo3[k] + hi3[k]), half = 0.5 * (hi3[k] - lo3[k]);
+          m.obb_half_out[k] = round_up(half + margin);
+          m.obb_half_in[k] = round_down(std::max(0., half - margin));
+          for (int a = 0; a < 3; a++) {
+            const double axv[3] = {ax[k].x, ax[k].y, ax[k].z};
+            m.obb_ax[k][a] = (float)axv[a];
+            m.obb_c[a] += (float)0.;  // (accumulated below in f64)
+          }
+          (void)centre_k;
+        }
+        double c3[3] = {0., 0., 0.};
+        for (int k = 0; k < 3; k++) {
+          const double centre_k = 0.5 * (lo3[k] + hi3[k]);
+          c3[0] += centre_k * ax[k].x; c3[1] += centre_k * ax[k].y; c3[2] += centre_k * ax[k].z;
+        }
+        for (int a = 0; a < 3; a++) m.obb_c[a] = (float)c3[a];
+      }
+    }
     for (int a = 0; a < 3; a++) { m.lo[a] = round_down(bx.lo[a] - pad); m.hi[a] = round_up(bx.hi[a] + pad); }
     {
       const double ex = (double)m.hi[0] - m.lo[0], ey = (double)m.hi[1] - m.lo[1], ez = (double)m.hi[2] - m.lo[2];

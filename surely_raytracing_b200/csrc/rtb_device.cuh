@@ -477,6 +477,7 @@ enum : int { PF_MISS = 0, PF_HIT = 1, PF_UNSURE = 2 };
 constexpr float PF_U = 5.9604645e-8f;  // 2^-24
 constexpr int CAND_K = 2;
 constexpr int CAND_OVERFLOW = 1;  // candidate-slot sentinel: "re-trace me exactly" (leaf references are negative)
+constexpr int CAND_CERTAIN = 2;   // in the SECOND slot: the first is the only candidate and a certain hit -- only its t is open
 
 struct PfRay {
   double ox, oy, oz;
@@ -621,20 +622,28 @@ RTB_DEV int prefilter_sphere(const double2* __restrict__ P, bool moving, const P
 // the (at most CAND_K) leaf references that can still hold the closest hit, each with the smallest t it could have
 struct Cands {
   int c0, c1;       // 0 = empty slot; CAND_OVERFLOW in c0 = more live candidates than slots
-  float lo0, lo1;
+  float lo0, lo1;   // smallest t each could have; the sign bit of the REFERENCE's complement is not used -- certainty
   float bound;      // smallest t_hi of a certain hit so far (+inf: none): nothing beyond it can be the closest hit
+  int certain;      // bit 0 / 1: slot 0 / 1 holds a certain hit (PF_HIT)
 };
-RTB_DEV void cands_reset(Cands& C) { C.c0 = 0; C.c1 = 0; C.lo0 = 0.f; C.lo1 = 0.f; C.bound = __int_as_float(0x7F800000); }
+RTB_DEV void cands_reset(Cands& C) { C.c0 = 0; C.c1 = 0; C.lo0 = 0.f; C.lo1 = 0.f; C.bound = __int_as_float(0x7F800000); C.certain = 0; }
 RTB_DEV void cands_add(Cands& C, int ref, int cls, float t_lo, float t_hi) {
   if (cls == PF_MISS || C.c0 == CAND_OVERFLOW) return;
   if (cls == PF_HIT && t_hi < C.bound) {
     C.bound = t_hi;
-    if (C.c1 != 0 && C.lo1 > C.bound) C.c1 = 0;
-    if (C.c0 != 0 && C.lo0 > C.bound) { C.c0 = C.c1; C.lo0 = C.lo1; C.c1 = 0; }
+    if (C.c1 != 0 && C.lo1 > C.bound) { C.c1 = 0; C.certain &= 1; }
+    if (C.c0 != 0 && C.lo0 > C.bound) { C.c0 = C.c1; C.lo0 = C.lo1; C.c1 = 0; C.certain >>= 1; }
   }
-  if (C.c0 == 0) { C.c0 = ref; C.lo0 = t_lo; }
-  else if (C.c1 == 0) { C.c1 = ref; C.lo1 = t_lo; }
+  const int cert = cls == PF_HIT ? 1 : 0;
+  if (C.c0 == 0) { C.c0 = ref; C.lo0 = t_lo; C.certain = cert; }
+  else if (C.c1 == 0) { C.c1 = ref; C.lo1 = t_lo; C.certain |= cert << 1; }
   else C.c0 = CAND_OVERFLOW;
+}
+// the candidate record that travels to the shade stage: {c0, c1}, with CAND_CERTAIN in the empty second slot when the
+// only candidate is a one-primitive leaf and a certain hit (then only its t has to be evaluated exactly)
+RTB_DEV void cands_record(const Cands& C, int& r0, int& r1) {
+  r0 = C.c0; r1 = C.c1;
+  if (C.c0 < 0 && C.c1 == 0 && (C.certain & 1) && leaf_count(C.c0) == 1) r1 = CAND_CERTAIN;
 }
 
 // classify the primitive(s) of one leaf and update the candidates.  MULTI as in test_leaf.
@@ -668,9 +677,22 @@ RTB_DEV int prefilter_leaf(const DScene& S, int leaf_ref, const PfRay& r, float 
 
 // exact resolution of the survivors (shade stage; every lane holds a ray): the reference-order f64 tests with the
 // reference's tie rule, on the candidates only.  MULTI as in test_leaf.
+// Quad::hit's t alone (src/object.rs:453-461, operation by operation): for a quad the traversal has already PROVEN to be
+// hit (t inside the interval, alpha / beta inside [0,1] beyond every rounding error) the planar coordinates decide nothing
+RTB_DEV double quad_t_only(const double2* __restrict__ P, const Ray& r) {
+  const double2 n01 = RTB_LDG(P + 0), n2d = RTB_LDG(P + 1);
+  const double denom = ddot(n01.x, n01.y, n2d.x, r.dx, r.dy, r.dz);
+  return dsub(n2d.y, ddot(n01.x, n01.y, n2d.x, r.ox, r.oy, r.oz)) / denom;
+}
+
 template <bool MULTI = true>
 RTB_DEV void resolve_candidates(const DScene& S, int c0, int c1, const Ray& r, double tmin, Hit& best) {
   hit_reset(best);
+  if (c1 == CAND_CERTAIN && (leaf_kind_bits(c0) & LEAF_KIND_QUAD)) {
+    best.prim = leaf_first(c0);
+    best.t = quad_t_only(S.prims + (size_t)best.prim * PRIM_D2, r);
+    return;
+  }
   if (c0 < 0) test_leaf<MULTI>(S, c0, r, tmin, best);
   if (c1 < 0) test_leaf<MULTI>(S, c1, r, tmin, best);
 }
@@ -738,6 +760,33 @@ RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded 
   const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
   const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
   return tn <= fmaf(fabsf(tf), 2e-6f, tf) + 1e-30f;
+}
+
+// Boundary = an oriented box (make_box under Translate / RotateY: cls_fast bit 10).  The medium's world-space AABB is
+// loose around a rotated box; in the box's own frame the slab test is tight.  fp32, conservative both ways:
+//   0  the whole LINE misses the box inflated by the margin: all six Quad::hit fail, both probes return None;
+//   2  both end points of [ta, tb] lie inside the box deflated by the margin (a box is convex): probe 1 over UNIVERSE
+//      returns the entry behind the origin (t1 < 0 < tmin), probe 2 the exit beyond tb -- the clamps of
+//      constant_medium.rs:58-63 then make the interval [tmin, tmax] whatever t1, t2 are;
+//   1  anything else: evaluate the quads.
+RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb) {
+  const float ex = (float)r.ox - m.obb_c[0], ey = (float)r.oy - m.obb_c[1], ez = (float)r.oz - m.obb_c[2];
+  const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz;
+  float tn = -3.0e38f, tf = 3.0e38f;
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float o = fmaf(ex, m.obb_ax[k][0], fmaf(ey, m.obb_ax[k][1], ez * m.obb_ax[k][2]));
+    const float d = fmaf(dx, m.obb_ax[k][0], fmaf(dy, m.obb_ax[k][1], dz * m.obb_ax[k][2]));
+    const float inv = safe_rcp(d);
+    const float t0 = (-m.obb_half_out[k] - o) * inv, t1 = (m.obb_half_out[k] - o) * inv;
+    tn = fmaxf(tn, fminf(t0, t1));
+    tf = fminf(tf, fmaxf(t0, t1));
+    inside = inside && fabsf(fmaf(ta, d, o)) < m.obb_half_in[k] && fabsf(fmaf(tb, d, o)) < m.obb_half_in[k];
+  }
+  if (inside) return 2;
+  // slack: 1e-5 relative on both ends of the interval (the slabs are already inflated by 1e-5 x scene magnitude)
+  return (tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf)) ? 1 : 0;
 }
 
 // BOXSCAN: compile the single-scan path for quad-only boundaries in.  The wavefront shade kernel instantiates
@@ -832,6 +881,11 @@ RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, dou
     const float pb = fmaf(tb, dx, ax), qb = fmaf(tb, dy, ay), rb = fmaf(tb, dz, az);
     const float da = fmaf(pa, pa, fmaf(qa, qa, ra * ra)), db = fmaf(pb, pb, fmaf(qb, qb, rb * rb));
     inside = da < m.sphere[3] && db < m.sphere[3];  // sphere[3] = r^2 shrunk by 1e-3 relative (flatten.cpp)
+  }
+  if (BOXSCAN && GENERIC && (m.cls_fast & 0x400)) {
+    const int where = medium_obb(m, r, (float)tmin, tmax < RTB_INF ? (float)tmax : 3.0e38f);
+    if (where == 0) return RTB_INF;
+    inside = where == 2 && tmax < RTB_INF;
   }
   if (inside) { t1 = -RTB_INF; t2 = RTB_INF; }
   else if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2)) return RTB_INF;
@@ -1309,6 +1363,12 @@ RTB_DEV bool shade(const DScene& S, const Tables& T, PathState& ps, const Event&
     const float wgt = fast_div(scattering_pdf, pdf_val);
     ps.bx *= atten.x * wgt; ps.by *= atten.y * wgt; ps.bz *= atten.z * wgt;
     if (!(S.flags & 2u) && ps.bx == 0.f && ps.by == 0.f && ps.bz == 0.f) return false;  // dead path: result is 0
+  }
+  if ((S.flags & 0x200u) && ps.bounce >= 3u) {  // RTB_FLAG_RUSSIAN_ROULETTE (opt-in; the reference has none)
+    const float q = fminf(1.f, fmaxf(0.05f, fmaxf(ps.bx, fmaxf(ps.by, ps.bz))));
+    if (!(rand4(S, ps.pixel, ps.sample, ps.bounce, 63u).x < q)) return false;
+    const float inv_q = fast_rcp(q);
+    ps.bx *= inv_q; ps.by *= inv_q; ps.bz *= inv_q;
   }
   ps.ray.ox = px; ps.ray.oy = py; ps.ray.oz = pz;  // Ray::new_timed(rec.p, dir, r.time())
   ps.ray.dx = (double)dir.x; ps.ray.dy = (double)dir.y; ps.ray.dz = (double)dir.z;

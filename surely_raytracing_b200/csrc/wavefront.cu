@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
     if (have && node == TRAV_DONE) {
       int2 h;
       if (CAND) {
-        h.x = cd.c0; h.y = cd.c1;
+        cands_record(cd, h.x, h.y);
         if (cd.c0 == CAND_OVERFLOW) Q.overflow[atomicAdd(&Q.c->n_overflow, 1)] = pos;
       } else {  // the winner as the only candidate: the shade stage repeats its test (bit-identical) for t
         h.x = 0; h.y = 0;
@@ -518,8 +518,11 @@ __device__ __forceinline__ void load_path(const RayRec* __restrict__ rays, int c
   unpack(a, b, c, d, p);
 }
 
-// Rays whose live candidates did not fit the slots (coplanar faces, grazing hits: ~0.1 % on c4): closest hit by the
+// Rays whose live candidates did not fit the slots (coplanar faces, grazing hits: ~0.05 % on c4): closest hit by the
 // exact traversal (closest_surface: fp32 cull, f64 leaves), the winner becomes the only candidate.
+// (67 us of mostly latency per iteration, 1.9 % of the step.  Folding the re-trace into k_wf_shade_rare -- so that it
+//  overlaps the deferred items -- was measured: 440.7 vs 438.3 ms per c4 step, no gain, and the re-traced rays would be
+//  shaded by another instantiation than in the exact-leaves arm, which costs the bit-identity of the two arms.)
 __global__ void __launch_bounds__(128) k_wf_extend_exact(const __grid_constant__ DScene S, WFQueues Q, const RayRec* __restrict__ rays_in) {
   const int n = Q.c->n_overflow;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1051,6 +1054,10 @@ __global__ void k_wf_trace_resolve(const __grid_constant__ DScene S, WFQueues Q,
   const int2 cand = Q.cands[i];
   Hit best;
   resolve_candidates<true>(S, cand.x, cand.y, r, 0.0001, best);
+  if (cand.y == CAND_CERTAIN && best.prim >= 0 && (leaf_kind_bits(cand.x) & LEAF_KIND_QUAD)) {
+    double tt;  // the full record wants (u, v) = (alpha, beta): the shade stage evaluates them only for uv-textured quads
+    quad_test(S.prims + (size_t)best.prim * PRIM_D2, r, -RTB_INF, RTB_INF, tt, best.a, best.b);
+  }
   RtbHit out;
   complete_hit(S, r, best, out);
   hits[i] = out;

@@ -130,7 +130,9 @@ int emu_trace_candidates(void* p, const RtbRay* rays, long long n, RtbHit* hits,
       Cands C;
       const float mag = fmaxf(S.scene_mag, (float)(fabs(r.ox) + fabs(r.oy) + fabs(r.oz)));
       if (closest_candidates<false>(S, r, mag, C, nullptr)) {
-        resolve_candidates<true>(S, C.c0, C.c1, r, 0.0001, best);
+        int r0, r1;
+        cands_record(C, r0, r1);
+        resolve_candidates<true>(S, r0, r1, r, 0.0001, best);
         resolved += (C.c0 < 0) + (C.c1 < 0);
         two += C.c1 < 0;
       } else {
@@ -229,6 +231,11 @@ extern "C" int emu_defer_ok(void* p) { return static_cast<Emu*>(p)->host.defer_o
 extern "C" int emu_leaf_roundtrip(int first, int count, int kind_bits) {
   const int ref = leaf_make(first, count, kind_bits);
   return ref < 0 && leaf_first(ref) == first && leaf_count(ref) == count && leaf_kind_bits(ref) == kind_bits;
+}
+// cls_fast of medium `mi` (bit 8: sphere boundary, bit 9: quads only, bit 10: oriented box recognised)
+extern "C" int emu_medium_flags(void* p, int mi) {
+  const HostScene& h = static_cast<Emu*>(p)->host;
+  return mi >= 0 && mi < (int)h.media.size() ? h.media[mi].cls_fast : -1;
 }
 // child references of inner node `node` of the BVH2 (device numbering)
 extern "C" void emu_node_children(void* p, int node, int* out2) {

@@ -41,6 +41,7 @@ def load():
         lib.emu_eval_texture.argtypes = [vp, C.c_int, vp, i64, vp]
         lib.emu_eval_light_pdf.argtypes = [vp, vp, i64, vp]
         lib.emu_spec_bits.argtypes = [vp]
+        lib.emu_medium_flags.argtypes = [vp, C.c_int]
         lib.emu_defer_ok.argtypes = [vp]
         lib.emu_check_leaf_refs.argtypes = [vp]
         lib.emu_check_qnodes.argtypes = [vp, vp, i64, i64, vp]

@@ -215,6 +215,12 @@ def test_scene_feature_bits_and_leaf_references(cfg, variant, expected):
     assert e.leaf_ref_violations() == 0
     # every non-solid texture of these scenes hangs off a Lambertian surface: the textured classes may be deferred
     assert e.defer_ok() == 1
+    from tests.emu.emu_lib import load
+    flags = [load().emu_medium_flags(e._h, mi) for mi in range(e.info.n_media)]
+    if cfg == "c3":   # Translate(RotateY(make_box)) boundaries are recognised as oriented boxes (tight fp32 cull, inside shortcut)
+        assert all(f & 0x200 and f & 0x400 for f in flags), flags
+    if cfg == "c4":   # sphere boundaries
+        assert all(f & 0x100 and not f & 0x400 for f in flags), flags
 
 
 def test_leaf_reference_codec():

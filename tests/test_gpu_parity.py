@@ -443,6 +443,43 @@ def test_sun_light_flag_and_auto_exposure_against_the_oracle():
     assert auto_expose(np.zeros((8, 8, 3)), 4) == 1.0 == orc.auto_expose(np.zeros((8, 8, 3)), 4)
 
 
+def test_checkpoint_resume_is_bit_identical_and_russian_roulette_is_unbiased(tmp_path):
+    """SURVEY 8f-4 extras.  (1) On-disk checkpoints: render [0, 25), save, load into a fresh scene, render [25, 64) ->
+    the very bits of one uninterrupted render (the accumulation buffer holds exact integer sums); a checkpoint of another
+    seed or size is refused.  (2) RTB_FLAG_RUSSIAN_ROULETTE (opt-in, not in the reference): fewer segments, and the image
+    still passes the variance-aware acceptance against the committed oracle render."""
+    import torch
+    b = BuiltScene("c2", width=120, spp=64)
+    g = Scene(b)
+    h, w = g.info.image_height, g.info.image_width
+    whole = torch.zeros((h, w, 4), dtype=torch.int64, device="cuda")
+    g.render_device(whole.data_ptr(), 0, 64, pipeline=capi.PIPELINE_WAVEFRONT)
+    part = torch.zeros_like(whole)
+    g.render_device(part.data_ptr(), 0, 25, pipeline=capi.PIPELINE_WAVEFRONT)
+    torch.cuda.synchronize()
+    ck = tmp_path / "c2.rtbck"
+    g.checkpoint_save(part.data_ptr(), ck)
+    assert ck.stat().st_size == 64 + h * w * 32
+    g2 = Scene(b)
+    resumed = torch.full_like(whole, 7)
+    g2.checkpoint_load(resumed.data_ptr(), ck)
+    g2.render_device(resumed.data_ptr(), 25, 64, pipeline=capi.PIPELINE_WAVEFRONT)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, resumed)
+    with pytest.raises(capi.RtbError):
+        Scene(BuiltScene("c2", width=120, spp=64, seed=5)).checkpoint_load(resumed.data_ptr(), ck)
+    with pytest.raises(capi.RtbError):
+        Scene(BuiltScene("c2", width=96, spp=64)).checkpoint_load(resumed.data_ptr(), ck)
+    gold = np.load(util.GOLDEN / "oracle_c3.npz")     # lights = empty: paths run to depth 10 unless they meet the light
+    n = int(gold["spp"])
+    plain, st_p = Scene(BuiltScene("c3", width=120, spp=n)).render(collect_stats=True)
+    rr, st_r = Scene(BuiltScene("c3", width=120, spp=n, flags=capi.RTB_FLAG_RUSSIAN_ROULETTE)).render(collect_stats=True)
+    assert st_r["segments"] < 0.8 * st_p["segments"]
+    ok, rep = util.image_acceptance(rr / n, n, gold["mean"].astype(np.float64), n, 1.6 * gold["var"].astype(np.float64))
+    assert ok, rep                                        # (roulette adds variance per path: the bound uses 1.6 sigma^2)
+    assert abs(rr.mean() - plain.mean()) < 0.01 * plain.mean()
+
+
 def test_render_multi_is_the_same_image_on_any_number_of_gpus():
     """rtb_render_multi = the reference seam on one box: contiguous slices of the stratum range on n GPUs (one thread,
     scene copy and stream each), ONE NCCL int64 sum-reduce, one D2H.  The image must not depend on n: bit-identical to

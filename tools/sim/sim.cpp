@@ -508,7 +508,9 @@ extern "C" int sim_candidates(void* p, const QRay* rays, long long n, int K, dou
     out[7] += (double)sc.prim_tests;
     if (!ok) { out[2]++; continue; }
     Hit best;
-    resolve_candidates<true>(S, C.c0, C.c1, r, 0.0001, best);
+    int r0, r1;
+    cands_record(C, r0, r1);
+    resolve_candidates<true>(S, r0, r1, r, 0.0001, best);
     out[3] += (C.c0 < 0) + (C.c1 < 0);
     out[6] += (C.c1 < 0);
     if (best.prim != exact.prim || best.t != exact.t) out[1]++;
