@@ -138,6 +138,7 @@ typedef struct RtbCamera {
 #define RTB_FLAG_QNODES 0x20u      /* 32-byte nodes with 16-bit quantised boxes (vetoed where the grid is coarse) */
 #define RTB_FLAG_BVH_LEAF4 0x40u   /* allow leaves of up to 4 primitives                                          */
 #define RTB_FLAG_NO_BOX_SCAN 0x80u /* quad-bounded media: two boundary probes as written instead of one scan      */
+#define RTB_FLAG_NO_BOX_LEAVES 0x400u /* axis-aligned make_box lists stay six one-quad leaves (A/B arm)          */
 /* The sun term of ray_color is commented out at HEAD (src/render.rs:300-308: `cam.background //+ sun_light`), so
  * `suns` is accepted and ignored (Q23).  This flag switches the term back on: a miss adds, for every sun,
  * Sun::_hit (src/object.rs:232-239): albedo if dot(unit(d), direction) > 1 - angular_diameter/180. */

@@ -19,7 +19,7 @@ RTB_ABI_VERSION = 2
 RTB_FLAG_ISO_PDF_ZERO = 1
 RTB_FLAG_PROPAGATE_NAN = 2
 RTB_FLAG_BVH4, RTB_FLAG_QNODES, RTB_FLAG_BVH_LEAF4, RTB_FLAG_NO_BOX_SCAN, RTB_FLAG_SUN_LIGHT = 0x10, 0x20, 0x40, 0x80, 0x100
-RTB_FLAG_RUSSIAN_ROULETTE = 0x200
+RTB_FLAG_RUSSIAN_ROULETTE, RTB_FLAG_NO_BOX_LEAVES = 0x200, 0x400
 RTB_TRACE_BRUTE_FORCE, RTB_TRACE_WAVEFRONT, RTB_TRACE_SECONDARY = 1, 2, 4
 (OPT_WF_CAPACITY, OPT_EXACT_LEAVES, OPT_SMEM_TOP, OPT_NO_DEFER_RARE, OPT_EXTEND_BLOCKS, OPT_FINISH_BELOW, OPT_PROFILE,
  OPT_MEGA_BELOW) = range(1, 9)

@@ -75,6 +75,9 @@ constexpr int BVH_MAX_LEAF = 4;   // primitives per leaf
 // bits describe the leaf's primitive when count == 1 (the builder's default), so the traversal can run
 // its test without touching prim_info -- one L1 wavefront less per test on a saturated L1 data pipe.
 constexpr int LEAF_KIND_QUAD = 1, LEAF_KIND_MOVING = 2;
+// Both bits set (quads never move): the leaf is an axis-aligned make_box -- count = 6 quads in face order -x +x -y +y -z +z,
+// the box bounds in the DPre slot of its first quad (DBoxBounds).  One slab test names the face a ray can hit first.
+constexpr int LEAF_KIND_BOX = 3;
 #if defined(__CUDACC__)
 #define RTB_HD __host__ __device__ inline
 #else
@@ -102,6 +105,8 @@ struct alignas(32) DPre {
   float ab1;           // max(|A|_1, |B|_1), rounded up: scales the error bound of alpha / beta
 };
 static_assert(sizeof(DPre) == 64, "DPre is read as one 256-bit f64 load + one 256-bit f32 load");
+struct alignas(32) DBoxBounds { double lo[3], hi[3], pad[2]; };  // in the DPre slot of a box leaf's first quad
+static_assert(sizeof(DBoxBounds) == sizeof(DPre), "DBoxBounds aliases a DPre slot");
 
 struct DMaterial {
   int kind;

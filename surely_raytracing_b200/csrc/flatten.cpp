@@ -2,6 +2,7 @@
 #include "flatten.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <chrono>
 #include <cstdio>
@@ -39,6 +40,7 @@ struct Xform {
 
 struct Baked {
   int kind, flags, material, xform, id;
+  int group = -1, face = 0;  // axis-aligned make_box: group id and face index (2 * axis + side), else -1
   double payload[PRIM_DOUBLES];
   double lo[3], hi[3];
 };
@@ -53,8 +55,61 @@ struct Builder {
   std::vector<int> medium_material;
   std::vector<double> medium_density;
   int next_id = 0;
+  int next_group = 0;
+  std::vector<std::array<double, 6>> group_bounds;  // per box group: the exact corner coordinates lo[3], hi[3]
 
   Builder(const RtbSceneDesc& d_, HostScene& o, std::string& e) : d(d_), out(o), err(e), seen(d_.n_objects, 0) {}
+
+  // Do the six surfaces [start, start + 6) form an axis-aligned box in world space -- make_box (src/object.rs:509-560)
+  // under no rotation?  Every quad edge along one axis, every corner coordinate EXACTLY one of the two bounds of its
+  // axis (so that a face's plane is the bound itself, bit for bit), every face present once.  Then they become one
+  // BVH leaf whose slab test names the face a ray can hit first (rtb_device.cuh, prefilter_box).
+  void detect_box(size_t start) {
+    double lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
+    for (size_t i = start; i < start + 6; i++) {
+      const Baked& b = surfaces[i];
+      if (b.kind != PRIM_QUAD) return;
+      const double* p = b.payload;
+      for (int c = 0; c < 4; c++)
+        for (int a = 0; a < 3; a++) {
+          const double x = p[4 + a] + ((c & 1) ? p[7 + a] : 0.) + ((c & 2) ? p[10 + a] : 0.);
+          lo[a] = std::min(lo[a], x); hi[a] = std::max(hi[a], x);
+        }
+    }
+    int faces[6], seen_faces = 0;
+    for (size_t i = start; i < start + 6; i++) {
+      const double* p = surfaces[i].payload;
+      int ua = -1, va = -1;
+      for (int a = 0; a < 3; a++) {
+        if (p[7 + a] != 0.) { if (ua >= 0) return; ua = a; }
+        if (p[10 + a] != 0.) { if (va >= 0) return; va = a; }
+      }
+      if (ua < 0 || va < 0 || ua == va) return;
+      const int k = 3 - ua - va;
+      for (int c = 0; c < 4; c++)
+        for (int a = 0; a < 3; a++) {
+          const double x = (p[4 + a] + ((c & 1) ? p[7 + a] : 0.)) + ((c & 2) ? p[10 + a] : 0.);
+          if (x != lo[a] && x != hi[a]) return;
+        }
+      if (p[4 + k] != lo[k] && p[4 + k] != hi[k]) return;
+      // the face must span the other two extents completely
+      for (int a : {ua, va}) {
+        const double e = a == ua ? p[7 + a] : p[10 + a];
+        if (std::min(p[4 + a], p[4 + a] + e) != lo[a] || std::max(p[4 + a], p[4 + a] + e) != hi[a]) return;
+      }
+      // the unit normal the reference computes must be the exact axis vector (n / |n| with two zero components)
+      if (std::fabs(p[k]) != 1. || p[(k + 1) % 3] != 0. || p[(k + 2) % 3] != 0.) return;
+      if (p[3] != p[k] * p[4 + k]) return;  // d = normal . q
+      const int f = 2 * k + (p[4 + k] == hi[k] ? 1 : 0);
+      if (lo[k] == hi[k]) return;
+      faces[i - start] = f;
+      seen_faces |= 1 << f;
+    }
+    if (seen_faces != 63) return;
+    for (size_t i = start; i < start + 6; i++) { surfaces[i].group = next_group; surfaces[i].face = faces[i - start]; }
+    group_bounds.push_back({lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]});
+    next_group++;
+  }
 
   bool fail(const std::string& m) { err = m; return false; }
 
@@ -127,8 +182,10 @@ struct Builder {
       case RTB_OBJ_LIST:
       case RTB_OBJ_BVH: {
         if (o.first < 0 || o.count < 0 || (long long)o.first + o.count > d.n_children) return fail("list child range out of bounds");
+        const size_t start = surfaces.size();
         for (int k = 0; k < o.count; k++)
           if (!walk(d.children[o.first + k], X, medium, depth + 1)) return false;
+        if (medium < 0 && o.count == 6 && surfaces.size() == start + 6 && !(d.flags & (RTB_FLAG_BVH_LEAF4 | RTB_FLAG_NO_BOX_LEAVES))) detect_box(start);
         return true;
       }
       case RTB_OBJ_TRANSLATE: {  // src/transform.rs:57-69
@@ -531,15 +588,45 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
     out.scene_mag = round_up(mag);
   }
 
-  BvhBuilder bvh(B.surfaces, (d.flags & RTB_FLAG_BVH_LEAF4) != 0);
+  // The BVH is built over ITEMS: a surface primitive, or an axis-aligned box group (six quads: one leaf).
+  std::vector<Baked> items;
+  std::vector<std::vector<int>> members;
+  {
+    std::vector<int> group_item(B.next_group, -1);
+    for (size_t i = 0; i < B.surfaces.size(); i++) {
+      const Baked& b = B.surfaces[i];
+      if (b.group < 0) { items.push_back(b); members.push_back({(int)i}); continue; }
+      if (group_item[b.group] < 0) {
+        group_item[b.group] = (int)items.size();
+        items.push_back(b);
+        members.push_back(std::vector<int>(6, -1));
+      }
+      Baked& it = items[group_item[b.group]];
+      for (int a = 0; a < 3; a++) { it.lo[a] = std::min(it.lo[a], b.lo[a]); it.hi[a] = std::max(it.hi[a], b.hi[a]); }
+      members[group_item[b.group]][b.face] = (int)i;
+    }
+  }
+  BvhBuilder bvh(items, (d.flags & RTB_FLAG_BVH_LEAF4) != 0);
   std::vector<int> node_remap;
-  if (!B.surfaces.empty()) bvh.build(0, (int)B.surfaces.size(), 0);
+  if (!items.empty()) bvh.build(0, (int)items.size(), 0);
   if (bvh.max_depth + 2 > BVH_STACK) { err = "BVH deeper than the traversal stack"; return RTB_ERR_UNSUPPORTED; }
   if (B.surfaces.size() >= (size_t)1 << 26) { err = "more than 2^26 surface primitives (leaf references hold 26 index bits)"; return RTB_ERR_UNSUPPORTED; }
   out.bvh_depth = bvh.max_depth;
   out.multi_leaf = 0;
   for (const BuildNode& bn : bvh.nodes) out.multi_leaf |= (bn.left < 0 && bn.count > 1) ? 1 : 0;
-  for (int i : bvh.order) emit_prim(d, out, B.surfaces[i]);
+  std::vector<int> item_first(items.size(), 0);  // emitted index of the first primitive of the item at each position of bvh.order
+  for (size_t pos = 0; pos < bvh.order.size(); pos++) {
+    item_first[pos] = (int)out.prim_info.size();
+    const std::vector<int>& mem = members[bvh.order[pos]];
+    for (int m : mem) emit_prim(d, out, B.surfaces[m]);
+    if (mem.size() == 6 && items[bvh.order[pos]].group >= 0) {  // the box bounds go into the DPre slot of the first face
+      DBoxBounds bb{};
+      const Baked& it = items[bvh.order[pos]];
+      for (int a = 0; a < 3; a++) { bb.lo[a] = B.group_bounds[it.group][a]; bb.hi[a] = B.group_bounds[it.group][3 + a]; }  // (not the padded AABB)
+      static_assert(sizeof(DBoxBounds) == sizeof(DPre), "");
+      std::memcpy(&out.pre[item_first[pos]], &bb, sizeof(bb));
+    }
+  }
   out.n_surface_prims = (int)B.surfaces.size();
 
   // Quantisation grid of the 32-byte nodes: 16-bit cell indices over the padded root box, per axis.
@@ -585,10 +672,11 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
   };
 
   // inner nodes get consecutive device indices in DFS order (root = 0)
-  auto leaf_ref = [&](int first, int count) {
-    const Baked& b0 = B.surfaces[bvh.order[first]];
+  auto leaf_ref = [&](int first, int count) {  // `first`, `count`: positions of bvh.order (items)
+    const Baked& b0 = items[bvh.order[first]];
+    if (b0.group >= 0) return leaf_make(item_first[first], 6, LEAF_KIND_BOX);  // (box groups only exist with one-item leaves)
     const int bits = (b0.kind == PRIM_QUAD ? LEAF_KIND_QUAD : 0) | ((b0.flags & PRIM_FLAG_MOVING) ? LEAF_KIND_MOVING : 0);
-    return leaf_make(first, count, bits);
+    return leaf_make(item_first[first], count, bits);
   };
   // Device indices of the inner nodes: the top TOP_LEVELS levels breadth-first (so that "the first k nodes" are the
   // top of the tree: what the shared-memory arm of the extend kernel stages), the subtrees below them depth-first

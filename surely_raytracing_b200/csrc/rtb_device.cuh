@@ -280,7 +280,9 @@ RTB_DEV void test_prim_k(const DScene& S, int pi, int kind_bits, const Ray& r, d
 template <bool MULTI = true>
 RTB_DEV int test_leaf(const DScene& S, int leaf_ref, const Ray& r, double tmin, Hit& best) {
   const int first = leaf_first(leaf_ref), count = leaf_count(leaf_ref);
-  if (!MULTI || count == 1) {
+  if (leaf_kind_bits(leaf_ref) == LEAF_KIND_BOX) {  // an axis-aligned make_box: its six quads, as the reference's List scans them
+    for (int i = 0; i < 6; i++) test_prim_k(S, first + i, LEAF_KIND_QUAD, r, tmin, best);
+  } else if (!MULTI || count == 1) {
     test_prim_k(S, first, leaf_kind_bits(leaf_ref), r, tmin, best);
   } else {
     for (int i = 0; i < count; i++) test_prim(S, first + i, r, tmin, best);
@@ -619,6 +621,72 @@ RTB_DEV int prefilter_sphere(const double2* __restrict__ P, bool moving, const P
   return t_lo > bound ? PF_MISS : PF_UNSURE;
 }
 
+// An axis-aligned make_box (src/object.rs:509-560: six quads) as ONE leaf.  Its faces are axis-aligned, so the
+// reference's Quad::hit of face (k, side) evaluates t = (plane_k - o_k) / d_k -- the normal is (+-1, 0, 0) exactly and the
+// zero terms of both dot products vanish -- and its alpha / beta test is "the hit point lies within the other two
+// slabs".  One slab test therefore names the only face that can be the closest hit: the ENTRY face when the box is
+// entered beyond t_min, the EXIT face when the origin lies inside (or on a face, heading in).  Every decision carries its
+// error window; anything ambiguous (edges, corners, grazing, t_min straddled, near-parallel entry) gives up:
+//   returns PF_MISS (no face can be the closest hit), PF_HIT (face index in `face`, t in [t_lo, t_hi]), or PF_UNSURE.
+RTB_DEV int prefilter_box(const DBoxBounds* __restrict__ bb, const PfRay& r, float tmin_lo, float tmin_hi, float bound, int& face,
+                          float& t_lo, float& t_hi) {
+  const D4 b0 = load_d4(reinterpret_cast<const double2*>(bb)), b1 = load_d4(reinterpret_cast<const double2*>(bb) + 2);
+  // (plane - o) in f64: a ray leaving a face of this very box must see that face at t ~ 1e-13, not ~ u |o| / |d|
+  const float ax = (float)(b0.a - r.ox), ay = (float)(b0.b - r.oy), az = (float)(b0.c - r.oz);
+  const float bx = (float)(b0.d - r.ox), by = (float)(b1.a - r.oy), bz = (float)(b1.b - r.oz);
+  const float ix = fast_rcp(r.dx), iy = fast_rcp(r.dy), iz = fast_rcp(r.dz);
+  // a direction component too small to divide by: parallel to that slab pair -- leave it to the exact tests
+  if (!(fabsf(r.dx) > 1e-7f && fabsf(r.dy) > 1e-7f && fabsf(r.dz) > 1e-7f)) {
+    // ... except an exactly zero component with the origin strictly outside that slab pair: the coordinate never
+    // changes, so no face of the other axes is hit within its extent, and the faces of this axis see denom == 0
+    const float e = r.num_err;
+    if ((r.dx == 0.f && (ax > e || bx < -e)) || (r.dy == 0.f && (ay > e || by < -e)) || (r.dz == 0.f && (az > e || bz < -e))) return PF_MISS;
+    return PF_UNSURE;
+  }
+  // near / far plane of each slab pair by the sign of the direction, each distance with its own window: 6 u relative
+  // (conversion, reciprocal, product, direction rounding) + the f64 rounding of the difference
+  const bool px = r.dx >= 0.f, py = r.dy >= 0.f, pz = r.dz >= 0.f;
+  const float n0 = (px ? ax : bx) * ix, f0 = (px ? bx : ax) * ix;
+  const float n1 = (py ? ay : by) * iy, f1 = (py ? by : ay) * iy;
+  const float n2 = (pz ? az : bz) * iz, f2 = (pz ? bz : az) * iz;
+  const float e0 = r.num_err * fabsf(ix) + 1e-30f, e1 = r.num_err * fabsf(iy) + 1e-30f, e2 = r.num_err * fabsf(iz) + 1e-30f;
+  const float wn0 = fmaf(6.f * PF_U, fabsf(n0), e0), wf0 = fmaf(6.f * PF_U, fabsf(f0), e0);
+  const float wn1 = fmaf(6.f * PF_U, fabsf(n1), e1), wf1 = fmaf(6.f * PF_U, fabsf(f1), e1);
+  const float wn2 = fmaf(6.f * PF_U, fabsf(n2), e2), wf2 = fmaf(6.f * PF_U, fabsf(f2), e2);
+  const float nlo0 = n0 - wn0, nlo1 = n1 - wn1, nlo2 = n2 - wn2, fhi0 = f0 + wf0, fhi1 = f1 + wf1, fhi2 = f2 + wf2;
+  const float tn_lo = fmaxf(nlo0, fmaxf(nlo1, nlo2)), tn_hi = fmaxf(n0 + wn0, fmaxf(n1 + wn1, n2 + wn2));
+  const float tf_hi = fminf(fhi0, fminf(fhi1, fhi2));
+  if (tn_lo > tf_hi) return PF_MISS;               // the line misses the box
+  if (tf_hi < tmin_lo) return PF_MISS;             // the box lies behind t_min
+  if (tn_lo > bound) return PF_MISS;               // ... or beyond a certain hit
+  // strictly inside the other two slabs at the hit: margins of one more window (a position margin >= num_err)
+  const float nin0 = fmaf(2.f, wn0, n0), nin1 = fmaf(2.f, wn1, n1), nin2 = fmaf(2.f, wn2, n2);
+  const float fin0 = fmaf(-2.f, wf0, f0), fin1 = fmaf(-2.f, wf1, f1), fin2 = fmaf(-2.f, wf2, f2);
+  if (tn_lo > tmin_hi) {                           // entered beyond t_min: the entry face, if it is unmistakable
+    const int k = (nlo0 >= nlo1 && nlo0 >= nlo2) ? 0 : (nlo1 >= nlo2 ? 1 : 2);
+    const float lo = k == 0 ? nlo0 : (k == 1 ? nlo1 : nlo2), hi = k == 0 ? n0 + wn0 : (k == 1 ? n1 + wn1 : n2 + wn2);
+    const float other_near = k == 0 ? fmaxf(nin1, nin2) : (k == 1 ? fmaxf(nin0, nin2) : fmaxf(nin0, nin1));
+    const float other_far = k == 0 ? fminf(fin1, fin2) : (k == 1 ? fminf(fin0, fin2) : fminf(fin0, fin1));
+    if (!(other_near < lo && hi < other_far)) return PF_UNSURE;  // an edge, a corner, or grazing
+    face = 2 * k + ((k == 0 ? px : (k == 1 ? py : pz)) ? 0 : 1);  // moving towards +k enters through the low plane
+    t_lo = lo; t_hi = hi;
+    return PF_HIT;
+  }
+  if (tn_hi < tmin_lo) {                           // origin inside, or on a face heading in: the exit face
+    const int k = (fhi0 <= fhi1 && fhi0 <= fhi2) ? 0 : (fhi1 <= fhi2 ? 1 : 2);
+    const float hi = k == 0 ? fhi0 : (k == 1 ? fhi1 : fhi2), lo = k == 0 ? f0 - wf0 : (k == 1 ? f1 - wf1 : f2 - wf2);
+    if (!(lo > tmin_hi)) return PF_UNSURE;
+    const float other_near = k == 0 ? fmaxf(nin1, nin2) : (k == 1 ? fmaxf(nin0, nin2) : fmaxf(nin0, nin1));
+    const float other_far = k == 0 ? fminf(fin1, fin2) : (k == 1 ? fminf(fin0, fin2) : fminf(fin0, fin1));
+    if (!(other_near < lo && hi < other_far)) return PF_UNSURE;
+    if (lo > bound) return PF_MISS;
+    face = 2 * k + ((k == 0 ? px : (k == 1 ? py : pz)) ? 1 : 0);  // moving towards +k leaves through the high plane
+    t_lo = lo; t_hi = hi;
+    return PF_HIT;
+  }
+  return PF_UNSURE;                                // t_min straddled by the entry
+}
+
 // the (at most CAND_K) leaf references that can still hold the closest hit, each with the smallest t it could have
 struct Cands {
   int c0, c1;       // 0 = empty slot; CAND_OVERFLOW in c0 = more live candidates than slots
@@ -651,6 +719,13 @@ template <bool MULTI = true>
 RTB_DEV int prefilter_leaf(const DScene& S, int leaf_ref, const PfRay& r, float tmin_lo, float tmin_hi, Cands& C) {
   const int first = leaf_first(leaf_ref), count = leaf_count(leaf_ref);
   float t_lo, t_hi;
+  if (leaf_kind_bits(leaf_ref) == LEAF_KIND_BOX) {
+    int face = 0;
+    const int cls = prefilter_box(reinterpret_cast<const DBoxBounds*>(S.pre + first), r, tmin_lo, tmin_hi, C.bound, face, t_lo, t_hi);
+    if (cls == PF_HIT) cands_add(C, leaf_make(first + face, 1, LEAF_KIND_QUAD), PF_HIT, t_lo, t_hi);
+    else if (cls == PF_UNSURE) C.c0 = CAND_OVERFLOW;  // (six possible faces do not fit two slots: the exact re-trace decides)
+    return 1;
+  }
   if (!MULTI || count == 1) {
     const int bits = leaf_kind_bits(leaf_ref);
     const double2* P = S.prims + (size_t)first * PRIM_D2;

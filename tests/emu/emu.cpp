@@ -256,6 +256,21 @@ extern "C" int emu_check_leaf_refs(void* p) {
       const int first = leaf_first(refs[c]), count = leaf_count(refs[c]);
       if (first < 0 || first + count > h.n_surface_prims) { bad++; continue; }
       const int4 info = h.prim_info[first];
+      if (leaf_kind_bits(refs[c]) == LEAF_KIND_BOX) {
+        // an axis-aligned make_box: six static quads in face order, face (k, side) on plane lo[k] / hi[k] of the bounds
+        // that sit in the DPre slot of the first face
+        DBoxBounds bb;
+        std::memcpy(&bb, &h.pre[first], sizeof(bb));
+        bad += count != 6;
+        for (int f = 0; f < 6 && count == 6; f++) {
+          const int4 fi = h.prim_info[first + f];
+          const double* P = &h.prims[(size_t)(first + f) * PRIM_DOUBLES];
+          const int k = f >> 1;
+          bad += (fi.x & 0xFF) != PRIM_QUAD || (fi.x & PRIM_FLAG_MOVING);
+          bad += P[4 + k] != ((f & 1) ? bb.hi[k] : bb.lo[k]) || P[7 + k] != 0. || P[10 + k] != 0.;
+        }
+        continue;
+      }
       const int want = ((info.x & 0xFF) == PRIM_QUAD ? LEAF_KIND_QUAD : 0) | ((info.x & PRIM_FLAG_MOVING) ? LEAF_KIND_MOVING : 0);
       bad += leaf_kind_bits(refs[c]) != want;
       const int mat = (info.x >> PRIM_MAT_SHIFT) & 0xFFF;

@@ -244,11 +244,31 @@ def test_multi_primitive_leaves_on_the_host_build():
     assert (hb["prim"] == he["prim"]).all() and np.array_equal(hb["t"], he["t"])
     hc, st = e.trace_candidates(rays)
     assert (hc["prim"] == he["prim"]).all() and np.array_equal(hc["t"], he["t"]) and st["overflows"] < 0.01 * len(rays)
-    b1 = BuiltScene("c4", width=96, spp=4)
+    b1 = BuiltScene("c4", width=96, spp=4, flags=capi.RTB_FLAG_NO_BOX_LEAVES)
     e1 = EmuScene(b1)
     assert e.info.n_bvh_nodes < 0.7 * e1.info.n_bvh_nodes
     h1 = e1.trace(rays)
     assert (h1["prim"] == he["prim"]).all() and np.array_equal(h1["t"], he["t"])
+
+
+def test_axis_aligned_boxes_become_one_leaf():
+    """Default build: each of the 400 make_box ground boxes of c4 (src/main.rs:439-463) is ONE leaf whose slab test
+    names the face; the tree shrinks by the 5 x 400 inner nodes and every hit -- exact arm, candidate arm, brute force,
+    the six-leaf build -- stays the same record."""
+    b = BuiltScene("c4", width=96, spp=4)
+    e = EmuScene(b)
+    e1 = EmuScene(BuiltScene("c4", width=96, spp=4, flags=capi.RTB_FLAG_NO_BOX_LEAVES))
+    assert e.leaf_ref_violations() == 0 and e1.leaf_ref_violations() == 0
+    assert e1.info.n_bvh_nodes - e.info.n_bvh_nodes == 5 * 400
+    rays = orc.OracleScene(b, use_bvh=False).camera_rays()
+    he, h1, hb = e.trace(rays), e1.trace(rays), e.trace(rays, capi.RTB_TRACE_BRUTE_FORCE)
+    hc, st = e.trace_candidates(rays)
+    for h in (h1, hb, hc):
+        assert (h["prim"] == he["prim"]).all() and np.array_equal(h["t"], he["t"]) and np.array_equal(h["normal"], he["normal"])
+    assert st["overflows"] < 0.005 * len(rays)
+    # the rotated boxes of c3 (RotateY) are not axis-aligned in world space: they stay six leaves
+    c3 = EmuScene(BuiltScene("c3", width=32, spp=4)); c3n = EmuScene(BuiltScene("c3", width=32, spp=4, flags=capi.RTB_FLAG_NO_BOX_LEAVES))
+    assert c3.info.n_bvh_nodes == c3n.info.n_bvh_nodes
 
 
 def test_top_levels_of_the_tree_come_first_in_memory():

@@ -11,6 +11,10 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from surely_raytracing_b200 import BuiltScene  # noqa: E402
+from surely_raytracing_b200 import capi  # noqa: E402
+
+NO_BOX = capi.RTB_FLAG_NO_BOX_LEAVES  # the prototypes scan primitives one by one through their DPre records
+
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libsim.so"
@@ -42,7 +46,7 @@ def main():
     lib.sim_collect.restype = C.c_longlong
     width = int(sys.argv[1]) if len(sys.argv) > 1 else 160
     cap = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
-    b = BuiltScene("c4", width=width)
+    b = BuiltScene("c4", width=width, flags=NO_BOX)
     h = C.c_void_p(lib.emu_scene_create(b.desc))
     cache = HERE / f"rays_w{width}_c{cap}.npy"
     if cache.exists():
@@ -88,7 +92,7 @@ def sort_experiment():
     lib = C.CDLL(str(LIB))
     lib.emu_scene_create.restype = C.c_void_p
     width, cap = 160, 32768
-    b = BuiltScene("c4", width=width)
+    b = BuiltScene("c4", width=width, flags=NO_BOX)
     h = C.c_void_p(lib.emu_scene_create(b.desc))
     rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
     base = dict(threshold=28, leaf_slots=1, stale_cull=0, break_mode=0, break_count=0, n_warps=64, cost_inner=80,
@@ -144,7 +148,7 @@ def check_q(width=160, cap=32768):
     lib = C.CDLL(str(LIB))
     lib.emu_scene_create.restype = C.c_void_p
     for cfg in ("c4", "c1", "c2", "c3", "c5"):
-        b = BuiltScene(cfg, width=width)
+        b = BuiltScene(cfg, width=width, flags=NO_BOX)
         h = C.c_void_p(lib.emu_scene_create(b.desc))
         if cfg == "c4":
             rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
@@ -179,7 +183,7 @@ def bvh4():
     build()
     lib = C.CDLL(str(LIB))
     lib.emu_scene_create.restype = C.c_void_p
-    b = BuiltScene("c4", width=160)
+    b = BuiltScene("c4", width=160, flags=NO_BOX)
     h = C.c_void_p(lib.emu_scene_create(b.desc))
     rays = np.load(HERE / "rays_w160_c32768.npy")
     base = dict(threshold=28, leaf_slots=1, stale_cull=0, break_mode=0, break_count=0, n_warps=64, cost_inner=80,
@@ -207,7 +211,7 @@ def prefilter(width=160, cap=32768):
     lib.emu_scene_create.restype = C.c_void_p
     lib.sim_collect.restype = C.c_longlong
     for cfg in ("c4", "c1", "c2", "c3", "c5"):
-        b = BuiltScene(cfg, width=width)
+        b = BuiltScene(cfg, width=width, flags=NO_BOX)
         h = C.c_void_p(lib.emu_scene_create(b.desc))
         if cfg == "c4" and (HERE / f"rays_w{width}_c{cap}.npy").exists():
             rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
@@ -236,7 +240,7 @@ def candidates(width=160, cap=32768):
     lib.emu_scene_create.restype = C.c_void_p
     lib.sim_collect.restype = C.c_longlong
     for cfg in ("c4", "c1", "c2", "c3", "c5"):
-        b = BuiltScene(cfg, width=width)
+        b = BuiltScene(cfg, width=width, flags=NO_BOX)
         h = C.c_void_p(lib.emu_scene_create(b.desc))
         if cfg == "c4" and (HERE / f"rays_w{width}_c{cap}.npy").exists():
             rays = np.load(HERE / f"rays_w{width}_c{cap}.npy")
