@@ -259,6 +259,9 @@ constexpr int WF_EXTEND_BLOCK = 128;
 #endif
 constexpr int WF_FETCH_THRESHOLD = WF_FETCH_THRESHOLD_N;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
+#ifndef WF_LEAF_PASSES
+#define WF_LEAF_PASSES 0  // measured on c4: kind-sorted passes 324 ms extend per step against 221 ms for the plain two-slot loop
+#endif
 #ifndef WF_BREAK_LEFT
 #define WF_BREAK_LEFT 16  // measured on c4: 0 -> 35.1, 12 -> 33.9, 16 -> 33.4, 20 -> 33.5, 24 -> 33.8 ms extend per step
 #endif
@@ -454,6 +457,29 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
     // ---- leaves: the postponed one, then the current node if it is a leaf too -------------------------
     if (CAND) {
       const PfRay pr = pf_ray(rox, roy, roz, rdx, rdy, rdz, rtime, S.scene_mag);
+#if WF_LEAF_PASSES
+      // Leaves by KIND, one pass per kind over both slots of every lane (the postponed leaf and the current node):
+      // a lane holding a sphere and a box joins the box pass with the box and the next pass with the sphere, instead of
+      // the warp running box code and sphere code for slot 0 and again for slot 1 at a handful of lanes each.
+      __syncwarp();
+      for (;;) {
+        const bool b0 = leaf < 0, b1 = node < 0;
+        const bool x0 = b0 && leaf_kind_bits(leaf) == LEAF_KIND_BOX, x1 = b1 && leaf_kind_bits(node) == LEAF_KIND_BOX;
+        const bool o0 = b0 && !x0, o1 = b1 && !x1;
+        const unsigned mb = __ballot_sync(FULL, x0 || x1), mo = __ballot_sync(FULL, o0 || o1);
+        if ((mb | mo) == 0u) break;
+        const bool box_pass = __popc(mb) >= __popc(mo);
+        int ref = 0;
+        if (box_pass ? x0 : o0) { ref = leaf; leaf = 0; }
+        else if (box_pass ? x1 : o1) { ref = node; WF_POP(); }
+        if (ref < 0) {
+          if (box_pass) prefilter_box_leaf(S, ref, pr, tmin_lo, tmin_hi, cd);
+          else prefilter_leaf<NODES == NODES_BVH2_MULTI>(S, ref, pr, tmin_lo, tmin_hi, cd);
+          if (STATS) st_prims += (unsigned long long)leaf_count(ref) / (box_pass ? 6 : 1);
+          if (cd.c0 == CAND_OVERFLOW) { leaf = 0; node = TRAV_DONE; }  // the exact kernel starts over
+        }
+      }
+#else
       while (leaf < 0) {
         const int count = prefilter_leaf<NODES == NODES_BVH2_MULTI>(S, leaf, pr, tmin_lo, tmin_hi, cd);
         if (STATS) st_prims += (unsigned long long)count;
@@ -463,6 +489,7 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
           WF_POP();
         }
       }
+#endif
       if (have) {
         tbest32 = cd.bound;
         if (cd.c0 == CAND_OVERFLOW) node = TRAV_DONE;  // the exact kernel starts over: nothing left to find here

@@ -309,6 +309,17 @@ def test_opt_in_tree_forms_give_the_same_image(cfg, flag):
         assert st_alt["node_visits"] < 0.75 * st_ref["node_visits"]
 
 
+def test_box_leaves_give_the_same_image():
+    """Default build: an axis-aligned make_box is one leaf whose slab test names the candidate face.  Against the build
+    with one leaf per quad (RTB_FLAG_NO_BOX_LEAVES): the same image bit for bit, on both extend arms."""
+    for cfg in ("c4", "c3"):
+        ref, _ = Scene(BuiltScene(cfg, width=160, spp=16, flags=capi.RTB_FLAG_NO_BOX_LEAVES)).render(pipeline=capi.PIPELINE_WAVEFRONT)
+        g = Scene(BuiltScene(cfg, width=160, spp=16))
+        assert ref.max() > 0 and np.array_equal(g.render(pipeline=capi.PIPELINE_WAVEFRONT)[0], ref), cfg
+        g.set_option(capi.OPT_EXACT_LEAVES, 1)
+        assert np.array_equal(g.render(pipeline=capi.PIPELINE_WAVEFRONT)[0], ref), cfg
+
+
 def test_multi_primitive_leaves_give_the_same_image():
     """RTB_FLAG_BVH_LEAF4 (a tuning arm of the builder) makes leaves of several primitives: the extend kernel then
     runs its generic-leaf instantiation and whole leaves travel as candidates.  Same closest hits, same image; fewer
@@ -317,7 +328,9 @@ def test_multi_primitive_leaves_give_the_same_image():
     g = Scene(BuiltScene("c4", width=160, spp=16, flags=capi.RTB_FLAG_BVH_LEAF4))
     alt, st = g.render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
     assert st["segments"] == st_ref["segments"] and st["prim_tests"] > 1.5 * st_ref["prim_tests"]
-    assert st["node_visits"] < st_ref["node_visits"]
+    _, st_six = Scene(BuiltScene("c4", width=160, spp=16, flags=capi.RTB_FLAG_NO_BOX_LEAVES)).render(pipeline=capi.PIPELINE_WAVEFRONT, collect_stats=True)
+    assert st["node_visits"] < st_six["node_visits"]   # (against one leaf per quad; the default's box leaves visit fewer still)
+    assert st_ref["node_visits"] < 0.9 * st_six["node_visits"] and st_ref["segments"] == st_six["segments"]
     # (another shade instantiation -- the generic one -- shades these paths: last-bit FMA differences part a few of them)
     rel = np.abs(alt - ref).max(axis=2) / (np.abs(ref).max(axis=2) + 1e-3)
     assert (rel > 1e-3).mean() < 2e-3 and abs(alt.mean() - ref.mean()) < 1e-5 * ref.mean()
