@@ -844,6 +844,7 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
           for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], dot(c, ax[k])); hi3[k] = std::max(hi3[k], dot(c, ax[k])); }
       }
       int faces = 0;
+      int face_of[6] = {0, 0, 0, 0, 0, 0};
       for (const Baked& b : q6) {
         const D3 n = vec(b.payload), q = vec(b.payload + 4), u = vec(b.payload + 7), v = vec(b.payload + 10);
         int k = -1;
@@ -859,10 +860,24 @@ int flatten_scene(const RtbSceneDesc& d, HostScene& out, std::string& err) {
         if (!(on_lo || on_hi)) { ok = false; break; }
         for (int a = 0; a < 3; a++)
           if (a != k && (std::fabs(cmin[a] - lo3[a]) > tol || std::fabs(cmax[a] - hi3[a]) > tol)) ok = false;
+        face_of[&b - q6.data()] = 2 * k + (on_hi ? 1 : 0);
         faces |= 1 << (2 * k + (on_hi ? 1 : 0));
       }
       if (ok && faces == 63) {
         m.cls_fast |= 0x400;
+        // the boundary records in FACE order (2 k + the +axis_k side): medium_obb names faces by this index
+        {
+          const size_t f0 = (size_t)m.first_prim;
+          const std::vector<double> prims6(out.prims.begin() + f0 * PRIM_DOUBLES, out.prims.begin() + (f0 + 6) * PRIM_DOUBLES);
+          const std::vector<DPre> pre6(out.pre.begin() + f0, out.pre.begin() + f0 + 6);
+          const std::vector<int4> info6(out.prim_info.begin() + f0, out.prim_info.begin() + f0 + 6);
+          for (int i = 0; i < 6; i++) {
+            const size_t dst = f0 + face_of[i];
+            std::copy(prims6.begin() + (size_t)i * PRIM_DOUBLES, prims6.begin() + (size_t)(i + 1) * PRIM_DOUBLES, out.prims.begin() + dst * PRIM_DOUBLES);
+            out.pre[dst] = pre6[i];
+            out.prim_info[dst] = info6[i];
+          }
+        }
         const double margin = 1e-5 * M;  // fp32 evaluation of the local coordinates at scene magnitude M errs by ~1e-6 M
         for (int k = 0; k < 3; k++) {
           const double centre_k = 0.5 * (lo3[k] + hi3[k]), half = 0.5 * (hi3[k] - lo3[k]);

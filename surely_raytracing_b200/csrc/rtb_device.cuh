@@ -861,11 +861,18 @@ RTB_DEV bool medium_line_cull(const DMedium& m, const Ray& r) {  // fp32 padded 
 //      returns the entry behind the origin (t1 < 0 < tmin), probe 2 the exit beyond tb -- the clamps of
 //      constant_medium.rs:58-63 then make the interval [tmin, tmax] whatever t1, t2 are;
 //   1  anything else: evaluate the quads.
-RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb) {
+//   3  (only when `faces` is asked for) as 1, and the ENTRY and EXIT face of the line are unmistakable: the planes of the
+//      true box lie between the deflated and the inflated ones, so each plane distance has an interval; the entry face is
+//      named when its interval lies above the other two near intervals and below the other two far intervals, likewise
+//      the exit face -- then Quad::hit succeeds on exactly these two faces (alpha / beta inside [0,1] by the margin,
+//      outside it on the other four) and their two t are the two probes' results.  The boundary primitives of such a
+//      medium are stored in face order (flatten.cpp): first_prim + 2 k + (the +axis_k side).
+RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb, bool faces, int& face_in, int& face_out) {
   const float ex = (float)r.ox - m.obb_c[0], ey = (float)r.oy - m.obb_c[1], ez = (float)r.oz - m.obb_c[2];
   const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz;
   float tn = -3.0e38f, tf = 3.0e38f;
   bool inside = true;
+  float nlo[3], nhi[3], flo[3], fhi[3], dk[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const float o = fmaf(ex, m.obb_ax[k][0], fmaf(ey, m.obb_ax[k][1], ez * m.obb_ax[k][2]));
@@ -875,18 +882,58 @@ RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb) {
     tn = fmaxf(tn, fminf(t0, t1));
     tf = fminf(tf, fmaxf(t0, t1));
     inside = inside && fabsf(fmaf(ta, d, o)) < m.obb_half_in[k] && fabsf(fmaf(tb, d, o)) < m.obb_half_in[k];
+    if (faces) {
+      const float A = -o * inv, ia = fabsf(inv);
+      const float out = m.obb_half_out[k] * ia, in = m.obb_half_in[k] * ia;
+      const float slack = 1e-6f * (fabsf(A) + out);  // rounding of the reciprocal, the products and an f64 direction
+      nlo[k] = A - out - slack; nhi[k] = A - in + slack;
+      flo[k] = A + in - slack; fhi[k] = A + out + slack;
+      dk[k] = d;
+    }
   }
   if (inside) return 2;
   // slack: 1e-5 relative on both ends of the interval (the slabs are already inflated by 1e-5 x scene magnitude)
-  return (tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf)) ? 1 : 0;
+  if (!(tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf))) return 0;
+  if (faces) {
+    const int ki = (nlo[0] >= nlo[1] && nlo[0] >= nlo[2]) ? 0 : (nlo[1] >= nlo[2] ? 1 : 2);
+    const int ko = (fhi[0] <= fhi[1] && fhi[0] <= fhi[2]) ? 0 : (fhi[1] <= fhi[2] ? 1 : 2);
+    bool sure = true;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      // entry point strictly inside the other slab pairs, exit point likewise; each named face alone on its side
+      if (j != ki) sure = sure && nhi[j] < nlo[ki] && nhi[ki] < flo[j];
+      if (j != ko) sure = sure && fhi[ko] < flo[j] && nhi[j] < flo[ko];
+    }
+    sure = sure && nhi[ki] < flo[ko] && fabsf(dk[ki]) > 1e-6f && fabsf(dk[ko]) > 1e-6f;
+    if (sure) {
+      face_in = 2 * ki + (dk[ki] >= 0.f ? 0 : 1);   // moving along +axis enters through the -axis face
+      face_out = 2 * ko + (dk[ko] >= 0.f ? 1 : 0);
+      return 3;
+    }
+  }
+  return 1;
 }
 
+#ifndef RTB_MEDIUM_FACES
+#define RTB_MEDIUM_FACES 1
+#endif
 // BOXSCAN: compile the single-scan path for quad-only boundaries in.  The wavefront shade kernel instantiates
 // both and picks per scene: the extra code costs the sphere-media headline scene (c4) 0.9 % through register
 // allocation alone, and gains the box-media scene (c3) 32 %.
+// face_in / face_out: the entry and exit face medium_obb named for this line (>= 0), -1 = not asked yet, -2 = asked, not certain
 template <bool BOXSCAN = true, bool GENERIC = true>
-RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, double& t1, double& t2) {
+RTB_DEV bool medium_interval(const DScene& S, const DMedium& m, const Ray& r, double& t1, double& t2, int face_in = -1, int face_out = -1) {
   if (!medium_line_cull(m, r)) return false;
+  if (BOXSCAN && GENERIC && RTB_MEDIUM_FACES && (m.cls_fast & 0x400)) {
+    if (face_in == -1 && medium_obb(m, r, 0.f, 0.f, true, face_in, face_out) != 3) face_in = -2;
+    if (face_in >= 0) {
+      // the two faces the line certainly crosses: probe 1 (UNIVERSE) returns the entry t, probe 2 over (t1 + 1e-4, inf)
+      // the exit t when it lies in that interval (constant_medium.rs:46-55) -- two plane distances instead of six quad tests
+      const double ta = quad_t_only(S.prims + (size_t)(m.first_prim + face_in) * PRIM_D2, r);
+      const double tb = quad_t_only(S.prims + (size_t)(m.first_prim + face_out) * PRIM_D2, r);
+      if (tb >= ta + 0.0001 && tb < RTB_INF && ta > -RTB_INF) { t1 = ta; t2 = tb; return true; }
+    }
+  }
   if (m.cls_fast & 0x100) {
     // boundary = one static sphere: both probes of constant_medium.rs:46-55 evaluate the SAME two roots
     // (Sphere::hit, object.rs:146-166), so compute them once -- bit-identical to two calls:
@@ -977,13 +1024,15 @@ RTB_DEV double medium_event(const DScene& S, const DMedium& m, const Ray& r, dou
     const float da = fmaf(pa, pa, fmaf(qa, qa, ra * ra)), db = fmaf(pb, pb, fmaf(qb, qb, rb * rb));
     inside = da < m.sphere[3] && db < m.sphere[3];  // sphere[3] = r^2 shrunk by 1e-3 relative (flatten.cpp)
   }
+  int face_in = -1, face_out = -1;
   if (BOXSCAN && GENERIC && (m.cls_fast & 0x400)) {
-    const int where = medium_obb(m, r, (float)tmin, tmax < RTB_INF ? (float)tmax : 3.0e38f);
+    const int where = medium_obb(m, r, (float)tmin, tmax < RTB_INF ? (float)tmax : 3.0e38f, RTB_MEDIUM_FACES != 0, face_in, face_out);
     if (where == 0) return RTB_INF;
     inside = where == 2 && tmax < RTB_INF;
+    if (where != 3) face_in = -2;
   }
   if (inside) { t1 = -RTB_INF; t2 = RTB_INF; }
-  else if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2)) return RTB_INF;
+  else if (!medium_interval<BOXSCAN, GENERIC>(S, m, r, t1, t2, face_in, face_out)) return RTB_INF;
   if (t1 < tmin) t1 = tmin;   // :58-60
   if (t2 > tmax) t2 = tmax;   // :61-63
   if (t1 >= t2) return RTB_INF;

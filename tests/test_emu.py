@@ -128,12 +128,12 @@ def test_medium_intervals_and_textures_and_light_pdf(monkeypatch):
             assert np.array_equal(np.isnan(a0), np.isnan(b0))
             ok = ~np.isnan(a0)
             assert np.allclose(a0[ok], b0[ok], rtol=1e-10, atol=1e-12) and np.allclose(a1[ok], b1[ok], rtol=1e-10, atol=1e-12)
-    # the single scan against the two probes as written (RTB_NO_BOX_SCAN=1 at scene creation): bit for bit, on
+    # the single scan against the two probes as written (RTB_FLAG_NO_BOX_SCAN): bit for bit, on
     # every ray set -- exact edges included, where the oracle itself may differ in the last bit because the
     # reference tests the box in its own rotated frame and the device in world space (instances)
-    monkeypatch.setenv("RTB_NO_BOX_SCAN", "1")
-    e3g = EmuScene(b3)
-    monkeypatch.delenv("RTB_NO_BOX_SCAN")
+    e3g = EmuScene(BuiltScene("c3", width=64, spp=4, flags=capi.RTB_FLAG_NO_BOX_SCAN))
+    from tests.emu.emu_lib import load as _load
+    assert _load().emu_medium_flags(e3._h, 0) & 0x400 and not (_load().emu_medium_flags(e3g._h, 0) & 0x600)
     for rays3 in (cam, inside, aimed):
         for m in range(2):
             b0, b1 = e3.medium_interval(m, rays3)

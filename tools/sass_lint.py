@@ -110,14 +110,33 @@ def lint(name, body):
                         escapes = True
         if not escapes:
             continue
+        # out-of-line subroutines (CALL.REL.NOINC targets: 64-bit division, f64 slow paths) sit behind the kernel's own
+        # code; what they write counts where they are CALLED, not where they are stored
+        subs = sorted({int(m2.group(1), 16) for _, x in body for m2 in [re.search(r"\bCALL\.REL\.NOINC\s+0x([0-9a-f]+)", x)] if m2})
+        first_sub = subs[0] if subs else None
+
+        def sub_writes(target):
+            out = []
+            for b2, x2 in body:
+                if b2 < target:
+                    continue
+                out.append((b2, x2))
+                if x2.startswith("RET"):
+                    break
+            return out
+
         for b, x in body:
             if b <= loop_end:
                 continue
+            if first_sub is not None and b >= first_sub:
+                break
             if re.match(r"(@!?U?P\d+\s+)?WARPSYNC(?!\.COLLECTIVE)", x):
                 break   # __syncwarp of the lanes that entered the loop: nobody runs ahead past this point
-            w, _ = ur_defs_uses(x)
-            for u in sorted(w & hoisted):
-                findings.append((a, end, u, b, x))
+            mc = re.search(r"\bCALL\.REL\.NOINC\s+0x([0-9a-f]+)", x)
+            for b2, x2 in ([(b, x)] if not mc else sub_writes(int(mc.group(1), 16))):
+                w, _ = ur_defs_uses(x2)
+                for u in sorted(w & hoisted):
+                    findings.append((a, end, u, b2, x2))
     return findings
 
 
