@@ -12,6 +12,8 @@ pub const RTB_FLAG_BVH_LEAF4: u32 = 0x40;
 pub const RTB_FLAG_NO_BOX_SCAN: u32 = 0x80;
 /// switches the sun term HEAD comments out (src/render.rs:300-308) back on
 pub const RTB_FLAG_SUN_LIGHT: u32 = 0x100;
+pub const RTB_FLAG_RUSSIAN_ROULETTE: u32 = 0x200;
+pub const RTB_FLAG_NO_BOX_LEAVES: u32 = 0x400;
 
 pub const OBJ_SPHERE: i32 = 0;
 pub const OBJ_QUAD: i32 = 1;
