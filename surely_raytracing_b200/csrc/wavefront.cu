@@ -259,8 +259,12 @@ constexpr int WF_EXTEND_BLOCK = 128;
 #endif
 constexpr int WF_FETCH_THRESHOLD = WF_FETCH_THRESHOLD_N;  // refill when fewer than this many lanes hold a ray
 constexpr int TRAV_DONE = 0x7FFFFFFF;
-#ifndef WF_LEAF_PASSES
-#define WF_LEAF_PASSES 0  // measured on c4: kind-sorted passes 324 ms extend per step against 221 ms for the plain two-slot loop
+#ifndef WF_DENSE_LEAVES
+// 1: the leaf references of a whole warp are classified through a shared-memory list, lane j taking entry j whoever owns it.
+// Measured on c4 (profiles/r02_leaf_phase_experiments.txt): extend 356 ms per step against 230 -- a round holds only ~15 leaf
+// references per warp, so the leaf code still runs at 6-9 lanes, and the list, ballots and barriers add 25 % instructions.
+// So did sorting the two slots of every lane into one pass per kind (box / sphere): 324 against 221.  Kept as the A/B arm.
+#define WF_DENSE_LEAVES 0
 #endif
 #ifndef WF_BREAK_LEFT
 #define WF_BREAK_LEFT 16  // measured on c4: 0 -> 35.1, 12 -> 33.9, 16 -> 33.4, 20 -> 33.5, 24 -> 33.8 ms extend per step
@@ -287,6 +291,8 @@ constexpr int TRAV_DONE = 0x7FFFFFFF;
 enum : int { NODES_BVH2 = 0, NODES_Q = 1, NODES_BVH4 = 2, NODES_BVH2_MULTI = 3, NODES_BVH2_SMEM = 4 };
 constexpr int WF_SMEM_NODES = 127;  // 7 complete levels of a balanced tree, 8 KB per block
 
+struct alignas(16) LeafRay { double ox, oy, oz; float dx, dy, dz, time; float pad, pad2; };  // 48 B: a lane's ray as the dense leaf phase reads it
+
 template <bool STATS, int NODES, bool CAND>
 __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_CAND : 8) k_wf_extend(const __grid_constant__ DScene S, WFQueues Q,
                                                                const RayRec* __restrict__ rays_in,
@@ -299,6 +305,10 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
     for (int k = threadIdx.x; k < 4 * n_top; k += blockDim.x) top_nodes[k] = __ldg(S.nodes + k);
     __syncthreads();
   }
+#if WF_DENSE_LEAVES
+  __shared__ LeafRay leaf_rays[CAND ? WF_EXTEND_BLOCK : 1];
+  __shared__ int4 leaf_list[CAND ? WF_EXTEND_BLOCK / 32 : 1][64];
+#endif
   const int n = Q.c->n_in, n_surv = Q.c->n_surv;
   unsigned long long st_nodes = 0, st_prims = 0;
   bool have = false, exhausted = false;
@@ -357,6 +367,13 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
             sr = NODES == NODES_Q ? slab_ray_q(S, rox, roy, roz, rdx, rdy, rdz) : slab_ray(rox, roy, roz, rdx, rdy, rdz);
             if (CAND) { cands_reset(cd); tbest32 = cd.bound; }
             else { hit_reset(best); tbest32 = __double2float_ru(best.t); }
+#if WF_DENSE_LEAVES
+            if (CAND) {
+              LeafRay lr;
+              lr.ox = rox; lr.oy = roy; lr.oz = roz; lr.dx = rdx; lr.dy = rdy; lr.dz = rdz; lr.time = rtime; lr.pad = 0.f;
+              leaf_rays[threadIdx.x] = lr;
+            }
+#endif
             sp = 0;
             leaf = 0;
             node = any_surface ? 0 : TRAV_DONE;
@@ -457,27 +474,54 @@ __global__ void __launch_bounds__(WF_EXTEND_BLOCK, CAND ? WF_EXTEND_MIN_BLOCKS_C
     // ---- leaves: the postponed one, then the current node if it is a leaf too -------------------------
     if (CAND) {
       const PfRay pr = pf_ray(rox, roy, roz, rdx, rdy, rdz, rtime, S.scene_mag);
-#if WF_LEAF_PASSES
-      // Leaves by KIND, one pass per kind over both slots of every lane (the postponed leaf and the current node):
-      // a lane holding a sphere and a box joins the box pass with the box and the next pass with the sphere, instead of
-      // the warp running box code and sphere code for slot 0 and again for slot 1 at a handful of lanes each.
+#if WF_DENSE_LEAVES
+      // Dense leaf phase: the leaf references of the whole warp (both slots of every lane, box leaves first) go to a
+      // per-warp list in shared memory, and lane j classifies entry j for whichever lane owns it -- the ray comes from
+      // the owner's shared-memory record, the result goes back through the list.  The leaf code then runs once per ~32
+      // entries at ~20 lanes instead of once per slot and kind at 6-8.
+      (void)pr;
       __syncwarp();
       for (;;) {
-        const bool b0 = leaf < 0, b1 = node < 0;
-        const bool x0 = b0 && leaf_kind_bits(leaf) == LEAF_KIND_BOX, x1 = b1 && leaf_kind_bits(node) == LEAF_KIND_BOX;
-        const bool o0 = b0 && !x0, o1 = b1 && !x1;
-        const unsigned mb = __ballot_sync(FULL, x0 || x1), mo = __ballot_sync(FULL, o0 || o1);
-        if ((mb | mo) == 0u) break;
-        const bool box_pass = __popc(mb) >= __popc(mo);
-        int ref = 0;
-        if (box_pass ? x0 : o0) { ref = leaf; leaf = 0; }
-        else if (box_pass ? x1 : o1) { ref = node; WF_POP(); }
-        if (ref < 0) {
-          if (box_pass) prefilter_box_leaf(S, ref, pr, tmin_lo, tmin_hi, cd);
-          else prefilter_leaf<NODES == NODES_BVH2_MULTI>(S, ref, pr, tmin_lo, tmin_hi, cd);
-          if (STATS) st_prims += (unsigned long long)leaf_count(ref) / (box_pass ? 6 : 1);
-          if (cd.c0 == CAND_OVERFLOW) { leaf = 0; node = TRAV_DONE; }  // the exact kernel starts over
+        const int L0 = leaf < 0 ? leaf : 0, L1 = node < 0 ? node : 0;
+        const bool b0 = L0 < 0 && leaf_kind_bits(L0) == LEAF_KIND_BOX, b1 = L1 < 0 && leaf_kind_bits(L1) == LEAF_KIND_BOX;
+        const bool o0 = L0 < 0 && !b0, o1 = L1 < 0 && !b1;
+        const unsigned mb0 = __ballot_sync(FULL, b0), mb1 = __ballot_sync(FULL, b1), mo0 = __ballot_sync(FULL, o0), mo1 = __ballot_sync(FULL, o1);
+        if ((mb0 | mb1 | mo0 | mo1) == 0u) break;
+        const int nb0 = __popc(mb0), nb = nb0 + __popc(mb1), no0 = __popc(mo0), E = nb + no0 + __popc(mo1);
+        const unsigned lt = (1u << lane) - 1u;
+        const int p0 = b0 ? __popc(mb0 & lt) : (o0 ? nb + __popc(mo0 & lt) : -1);
+        const int p1 = b1 ? nb0 + __popc(mb1 & lt) : (o1 ? nb + no0 + __popc(mo1 & lt) : -1);
+        int4* ent = leaf_list[threadIdx.x >> 5];
+        if (p0 >= 0) ent[p0] = make_int4(L0, lane, __float_as_int(cd.bound), 0);
+        if (p1 >= 0) ent[p1] = make_int4(L1, lane, __float_as_int(cd.bound), 0);
+        __syncwarp();
+        for (int base = 0; base < E; base += 32) {
+          const int e = base + lane;
+          if (e < E) {
+            const int4 en = ent[e];
+            const LeafRay lr = leaf_rays[(threadIdx.x & ~31) + en.y];
+            const PfRay wr = pf_ray(lr.ox, lr.oy, lr.oz, lr.dx, lr.dy, lr.dz, lr.time, S.scene_mag);
+            int ref = 0;
+            float t_lo = 0.f, t_hi = 0.f;
+            const int cls = prefilter_classify<NODES == NODES_BVH2_MULTI>(S, en.x, wr, tmin_lo, tmin_hi, __int_as_float(en.z), ref, t_lo, t_hi);
+            ent[e] = make_int4(cls, ref, __float_as_int(t_lo), __float_as_int(t_hi));
+          }
         }
+        __syncwarp();
+        if (p0 >= 0) {
+          const int4 r0 = ent[p0];
+          cands_apply(cd, r0.x, r0.y, __int_as_float(r0.z), __int_as_float(r0.w));
+          if (STATS) st_prims += (unsigned long long)(b0 ? 1 : leaf_count(L0));
+          leaf = 0;
+        }
+        if (p1 >= 0) {
+          const int4 r1 = ent[p1];
+          cands_apply(cd, r1.x, r1.y, __int_as_float(r1.z), __int_as_float(r1.w));
+          if (STATS) st_prims += (unsigned long long)(b1 ? 1 : leaf_count(L1));
+          WF_POP();
+        }
+        if (cd.c0 == CAND_OVERFLOW) { leaf = 0; node = TRAV_DONE; }  // the exact kernel starts over
+        __syncwarp();  // the list is rewritten by the next round
       }
 #else
       while (leaf < 0) {
