@@ -51,10 +51,10 @@ I_CONST = {"box": 19.0, "prim": 31.0, "medium": 97.0, "shade": 145.0, "light": 6
 PEAK_LANE_INSTR_PER_CLK_PER_SM = 128
 # ncu counters of the FINAL binary (profiles/r02_*): executed thread-instructions per segment of the two hot kernels,
 # their lanes per warp instruction, and DRAM bytes per segment over every k_wf_* launch of the bench command.
-NCU = {"source": "profiles/r01b_wavefront_ncu_key_counters.txt (r02 capture pending)",
-       "thread_instr_per_segment": {"k_wf_extend": 1166.0, "k_wf_shade": 739.0},
-       "lanes": {"k_wf_extend": 16.6, "k_wf_shade": 20.1},
-       "dram_bytes_per_segment_c4": 204.1}
+NCU = {"source": "profiles/r02_launch_summary.txt (ncu launch list of this command on the final binary; tools/ncu_constants.py)",
+       "thread_instr_per_segment": {"k_wf_extend": 1069.6, "k_wf_shade": 860.1},
+       "lanes": {"k_wf_extend": 16.28, "k_wf_shade": 21.54},
+       "dram_bytes_per_segment_c4": 199.0}
 
 
 def algorithmic_instr(st, n_lights):

@@ -12,5 +12,9 @@ echo "full iteration rc=$?"
 timeout 600 $CMD --option 2=1 > gpurun_out/plain_c.log 2>&1 &&
 timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_wf_extend<' -s 140 -c 1 -f -o gpurun_out/r02_extend_exact_arm $CMD --option 2=1 > gpurun_out/ncu_c.log 2>&1
 echo "exact arm rc=$?"
-tail -1 gpurun_out/plain_a.log | cut -c1-200
+timeout 600 $CMD --flags 0x400 > gpurun_out/plain_d.log 2>&1 &&
+timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_wf_extend<' -s 140 -c 1 -f -o gpurun_out/r02_extend_sixleaf_arm $CMD --flags 0x400 > gpurun_out/ncu_d.log 2>&1
+echo "six-leaf arm rc=$?"
+for f in a b c d; do tail -1 gpurun_out/plain_$f.log | cut -c1-160; done
+cp surely_raytracing_b200/librtb200.so gpurun_out/librtb200_profiled.so
 ls -la gpurun_out/*.ncu-rep gpurun_out/r02_launches.csv
