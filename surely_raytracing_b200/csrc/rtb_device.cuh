@@ -907,7 +907,7 @@ RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb, bool 
   const float dx = (float)r.dx, dy = (float)r.dy, dz = (float)r.dz;
   float tn = -3.0e38f, tf = 3.0e38f;
   bool inside = true;
-  float nlo[3], nhi[3], flo[3], fhi[3], dk[3];
+  float nlo[3], nhi[3], flo[3], fhi[3], dk[3];  // (statically indexed only: registers)
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const float o = fmaf(ex, m.obb_ax[k][0], fmaf(ey, m.obb_ax[k][1], ez * m.obb_ax[k][2]));
@@ -930,19 +930,18 @@ RTB_DEV int medium_obb(const DMedium& m, const Ray& r, float ta, float tb, bool 
   // slack: 1e-5 relative on both ends of the interval (the slabs are already inflated by 1e-5 x scene magnitude)
   if (!(tn - 1e-5f * fabsf(tn) <= tf + 1e-5f * fabsf(tf))) return 0;
   if (faces) {
-    const int ki = (nlo[0] >= nlo[1] && nlo[0] >= nlo[2]) ? 0 : (nlo[1] >= nlo[2] ? 1 : 2);
-    const int ko = (fhi[0] <= fhi[1] && fhi[0] <= fhi[2]) ? 0 : (fhi[1] <= fhi[2] ? 1 : 2);
-    bool sure = true;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      // entry point strictly inside the other slab pairs, exit point likewise; each named face alone on its side
-      if (j != ki) sure = sure && nhi[j] < nlo[ki] && nhi[ki] < flo[j];
-      if (j != ko) sure = sure && fhi[ko] < flo[j] && nhi[j] < flo[ko];
-    }
-    sure = sure && nhi[ki] < flo[ko] && fabsf(dk[ki]) > 1e-6f && fabsf(dk[ko]) > 1e-6f;
+    // entry axis: the one whose near interval lies wholly above the other two (at most one can); exit axis likewise below
+    const bool e0 = nlo[0] > fmaxf(nhi[1], nhi[2]), e1 = nlo[1] > fmaxf(nhi[0], nhi[2]), e2 = nlo[2] > fmaxf(nhi[0], nhi[1]);
+    const bool x0 = fhi[0] < fminf(flo[1], flo[2]), x1 = fhi[1] < fminf(flo[0], flo[2]), x2 = fhi[2] < fminf(flo[0], flo[1]);
+    const float nhi_in = e0 ? nhi[0] : (e1 ? nhi[1] : nhi[2]), d_in = e0 ? dk[0] : (e1 ? dk[1] : dk[2]);
+    const float flo_out = x0 ? flo[0] : (x1 ? flo[1] : flo[2]), d_out = x0 ? dk[0] : (x1 ? dk[1] : dk[2]);
+    // the entry point strictly inside every far plane, the exit point strictly beyond every near plane (for the named
+    // axis itself that only asks for a box thicker than the margin)
+    const bool sure = (e0 || e1 || e2) && (x0 || x1 || x2) && nhi_in < fminf(flo[0], fminf(flo[1], flo[2])) &&
+                      fmaxf(nhi[0], fmaxf(nhi[1], nhi[2])) < flo_out && fabsf(d_in) > 1e-6f && fabsf(d_out) > 1e-6f;
     if (sure) {
-      face_in = 2 * ki + (dk[ki] >= 0.f ? 0 : 1);   // moving along +axis enters through the -axis face
-      face_out = 2 * ko + (dk[ko] >= 0.f ? 1 : 0);
+      face_in = (e0 ? 0 : (e1 ? 2 : 4)) + (d_in >= 0.f ? 0 : 1);   // moving along +axis enters through the -axis face
+      face_out = (x0 ? 0 : (x1 ? 2 : 4)) + (d_out >= 0.f ? 1 : 0);
       return 3;
     }
   }
