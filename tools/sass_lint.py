@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS lint for the ptxas hazard that produced round 1's "illegal memory access" in the fused trace kernel.
 
-What happened there (cuda-gdb, gpurun_out/repro_old_gdb2.log; DESIGN.md "The -O3 fault"): ptxas 12.9 hoisted the
+What happened there (cuda-gdb, profiles/r02_o3_fault_cuda_gdb.txt): ptxas 12.9 hoisted the
 loop-invariant address `prims + 0x30` into the UNIFORM register pair UR5:UR6 before the divergent BVH traversal loop
 (a BSSY.RELIABLE region that lanes leave one by one through `BREAK.RELIABLE` + a branch past the BSYNC), and re-used UR5
 for an f64 immediate (`UMOV UR5, 0x3fd45f30`, a coefficient of the atan2 polynomial) in the code after the loop.  Uniform
