@@ -235,17 +235,23 @@ struct BuildNode {
   int first = 0, count = 0;    // leaf range in the ordered primitive index array
 };
 
+struct BuildBounds { double lo[3], hi[3]; };  // what the builder reads of an item, packed (the Baked records are 4x larger: cache misses)
+
 struct BvhBuilder {
-  const std::vector<Baked>& prims;
+  std::vector<BuildBounds> prims;
   std::vector<int> order;
   std::vector<BuildNode> nodes;
   int max_depth = 0;
   std::vector<std::pair<double, int>> keyed;  // scratch of the exact sweep
   std::vector<double> sweep_area;
+  std::vector<int> part_scratch;              // right-hand side of the stable partition
+  double bin_cmin[3], bin_cmax[3];            // centroid range of the node being split (binned search -> partition)
   double kTraversal = 1.0, kIntersect = 3.0;  // SAH costs
   int max_leaf = 1;  // measured on c4: one primitive per leaf, Ci/Ct = 3 -> fewest f64 tests (profiles/r01_bvh_sweep.txt)
 
-  BvhBuilder(const std::vector<Baked>& p, bool leaves_of_4) : prims(p), order(p.size()) {
+  BvhBuilder(const std::vector<Baked>& p, bool leaves_of_4) : prims(p.size()), order(p.size()) {
+    for (size_t i = 0; i < p.size(); i++)
+      for (int a = 0; a < 3; a++) { prims[i].lo[a] = p[i].lo[a]; prims[i].hi[a] = p[i].hi[a]; }
     std::iota(order.begin(), order.end(), 0);
     if (leaves_of_4) { max_leaf = 4; kIntersect = 0.7; }  // RTB_FLAG_BVH_LEAF4: the tuning arm of profiles/r01_bvh_sweep.txt
   }
@@ -275,48 +281,56 @@ struct BvhBuilder {
         std::sort(keyed.begin(), keyed.begin() + count);
         Box rb;
         for (int i = count - 1; i > 0; i--) {
-          const Baked& p = prims[order[first + keyed[i].second]];
+          const BuildBounds& p = prims[order[first + keyed[i].second]];
           rb.grow(p.lo, p.hi);
           sweep_area[i] = rb.area();
         }
         Box lb;
         for (int i = 1; i < count; i++) {
-          const Baked& p = prims[order[first + keyed[i - 1].second]];
+          const BuildBounds& p = prims[order[first + keyed[i - 1].second]];
           lb.grow(p.lo, p.hi);
           const double cost = lb.area() * i + sweep_area[i] * (count - i);
           if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
         }
       }
     } else {
+      // one pass for the centroid range of all three axes, one pass for all three binnings, then a sweep per axis
       constexpr int NB = 32;
+      for (int a = 0; a < 3; a++) { bin_cmin[a] = kInf; bin_cmax[a] = -kInf; }
+      for (int i = 0; i < count; i++) {
+        const BuildBounds& p = prims[order[first + i]];
+        for (int a = 0; a < 3; a++) {
+          const double c = p.lo[a] + p.hi[a];
+          bin_cmin[a] = std::min(bin_cmin[a], c); bin_cmax[a] = std::max(bin_cmax[a], c);
+        }
+      }
+      Box bins[3][NB];
+      int cnt[3][NB] = {};
+      double scale3[3];
+      for (int a = 0; a < 3; a++) scale3[a] = bin_cmax[a] > bin_cmin[a] ? NB / (bin_cmax[a] - bin_cmin[a]) : 0.;
+      for (int i = 0; i < count; i++) {
+        const BuildBounds& p = prims[order[first + i]];
+        for (int a = 0; a < 3; a++) {
+          if (scale3[a] == 0.) continue;
+          int bi = (int)((p.lo[a] + p.hi[a] - bin_cmin[a]) * scale3[a]);
+          bi = bi < 0 ? 0 : (bi >= NB ? NB - 1 : bi);
+          bins[a][bi].grow(p.lo, p.hi);
+          cnt[a][bi]++;
+        }
+      }
       for (int axis = 0; axis < 3; axis++) {
-        double cmin = kInf, cmax = -kInf;
-        for (int i = 0; i < count; i++) {
-          const Baked& p = prims[order[first + i]];
-          const double c = p.lo[axis] + p.hi[axis];
-          cmin = std::min(cmin, c); cmax = std::max(cmax, c);
-        }
-        if (!(cmax > cmin)) continue;
-        Box bins[NB];
-        int cnt[NB] = {0};
-        const double scale = NB / (cmax - cmin);
-        for (int i = 0; i < count; i++) {
-          const Baked& p = prims[order[first + i]];
-          int b = (int)((p.lo[axis] + p.hi[axis] - cmin) * scale);
-          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-          bins[b].grow(p.lo, p.hi);
-          cnt[b]++;
-        }
+        if (scale3[axis] == 0.) continue;
+        const double cmin = bin_cmin[axis], scale = scale3[axis];
         double right_area[NB];
         int right_cnt[NB];
         Box rb;
         int rc = 0;
-        for (int b = NB - 1; b > 0; b--) { if (cnt[b]) rb.grow(bins[b].lo, bins[b].hi); rc += cnt[b]; right_area[b] = rb.area(); right_cnt[b] = rc; }
+        for (int b = NB - 1; b > 0; b--) { if (cnt[axis][b]) rb.grow(bins[axis][b].lo, bins[axis][b].hi); rc += cnt[axis][b]; right_area[b] = rb.area(); right_cnt[b] = rc; }
         Box lb;
         int lc = 0;
         for (int b = 1; b < NB; b++) {
-          if (cnt[b - 1]) lb.grow(bins[b - 1].lo, bins[b - 1].hi);
-          lc += cnt[b - 1];
+          if (cnt[axis][b - 1]) lb.grow(bins[axis][b - 1].lo, bins[axis][b - 1].hi);
+          lc += cnt[axis][b - 1];
           if (lc == 0 || right_cnt[b] == 0) continue;
           const double cost = lb.area() * lc + right_area[b] * right_cnt[b];
           if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = lc; best_plane = cmin + b / scale; }
@@ -332,21 +346,20 @@ struct BvhBuilder {
     if (count <= max_leaf && leaf_cost <= split_cost) return self;
     if (binned && best_plane != 0.) {
       // same bin assignment as the search (so the counts match), order inside each side kept
-      double cmin = kInf, cmax = -kInf;
-      for (int i = 0; i < count; i++) {
-        const Baked& p = prims[order[first + i]];
-        const double c = p.lo[best_axis] + p.hi[best_axis];
-        cmin = std::min(cmin, c); cmax = std::max(cmax, c);
-      }
+      const double cmin = bin_cmin[best_axis], cmax = bin_cmax[best_axis];
       const double scale = 32 / (cmax - cmin);
       const int split_bin = (int)std::lround((best_plane - cmin) * scale);
-      auto left_side = [&](int a) {
+      if ((int)part_scratch.size() < count) part_scratch.resize(count);
+      int nl = 0, nr = 0;
+      for (int i = 0; i < count; i++) {
+        const int a = order[first + i];
         int b = (int)((prims[a].lo[best_axis] + prims[a].hi[best_axis] - cmin) * scale);
         b = b < 0 ? 0 : (b >= 32 ? 31 : b);
-        return b < split_bin;
-      };
-      auto mid = std::stable_partition(order.begin() + first, order.begin() + first + count, left_side);
-      best_split = (int)(mid - (order.begin() + first));
+        if (b < split_bin) order[first + nl++] = a;  // (nl <= i: never overwrites an unread entry)
+        else part_scratch[nr++] = a;
+      }
+      std::copy(part_scratch.begin(), part_scratch.begin() + nr, order.begin() + first + nl);
+      best_split = nl;
       if (best_split <= 0 || best_split >= count) {  // numerical corner: fall back to a median split
         std::stable_sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
           return prims[a].lo[best_axis] + prims[a].hi[best_axis] < prims[b].lo[best_axis] + prims[b].hi[best_axis];
