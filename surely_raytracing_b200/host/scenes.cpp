@@ -290,6 +290,37 @@ FlatScene* furnace(int width, int spp, int depth) {
   return new FlatScene(cam, world, nullptr);
 }
 
+// Not a reference scene: a stress case for the box leaves of the traversal (csrc/rtb_device.cuh, prefilter_box) built with the
+// reference's own make_box -- boxes that share whole faces and edges, a box inside a box, spheres inside and through boxes, a
+// translated box (its baked corners need not agree bit for bit: it must quietly stay six leaves), a rotated one, the camera
+// INSIDE a large glass box, a light box.
+FlatScene* box_city(int width, int spp, int depth) {
+  HittableList world;
+  Material grey = Lambertian::new_(Color(0.6, 0.6, 0.6)), red = Lambertian::new_(Color(0.7, 0.2, 0.2));
+  Material glass = Dielectric::new_(1.5, Color(1., 1., 1.)), steel = Metal::new_(Color(0.8, 0.8, 0.9), 0.1);
+  Material lamp = DiffuseLight::new_(Color(6., 6., 5.));
+  HittableList blocks;
+  for (int i = -3; i < 3; i++)
+    for (int k = -3; k < 3; k++) {  // a 6 x 6 block of towers that touch along whole faces, heights on a fixed pattern
+      const double h = 1. + (double)((i * 7 + k * 13 + 80) % 5);
+      blocks.add(make_box(Point3(2. * i, 0., 2. * k), Point3(2. * i + 2., h, 2. * k + 2.), ((i + k) & 1) ? grey : red));
+    }
+  world.add(ObjectList(blocks.create_bvh()));
+  world.add(make_box(Point3(-6., -1., -6.), Point3(6., 0., 6.), grey));                     // a slab under all of them (shared plane y = 0)
+  world.add(make_box(Point3(-0.5, 5.5, -0.5), Point3(0.5, 6.5, 0.5), lamp));                // a light box above the tallest tower
+  world.add(make_box(Point3(-9., 0., -9.), Point3(9., 12., 9.), glass));                    // everything, camera included, inside a glass box
+  world.add(make_box(Point3(6.5, 0., -1.), Point3(8.5, 2., 1.), steel));
+  world.add(make_box(Point3(7., 0.5, -0.5), Point3(8., 1.5, 0.5), red));                     // a box inside a box
+  world.add(Sphere::new_(Point3(7.5, 1., 0.), 0.3, lamp));                                  // a lamp inside both
+  world.add(Sphere::new_(Point3(-7.5, 1., 0.), 1.2, glass));
+  world.add(make_box(Point3(-8., 0., -0.5), Point3(-7., 1., 0.5), steel));                   // a box through that sphere
+  world.add(Translate::new_(make_box(Point3(0., 0., 0.), Point3(1.1, 0.7, 1.3), red), Vec3(0.1, 6.2, 7.3)));
+  world.add(Translate::new_(RotateY::new_(make_box(Point3(0., 0., 0.), Point3(1., 2., 1.), grey), 30.), Vec3(-7.5, 0., 6.5)));
+  Camera cam = Camera::new_(1., pick(width, 200), pick(spp, 64), pick(depth, 12), 70., Point3(5.2, 7.5, 8.1),
+                            Point3(0., 2., 0.), Vec3(0., 1., 0.), 0., 10., Color(0.3, 0.4, 0.6));
+  return new FlatScene(cam, world, nullptr);
+}
+
 }  // namespace
 
 extern "C" {
@@ -315,6 +346,7 @@ void* rtbs_build(const char* name, int width, int spp, int depth, uint64_t seed,
     else if (n == "quads") f = quads(width, spp, depth);
     else if (n == "simple_light") f = simple_light(width, spp, depth, variant);
     else if (n == "furnace") f = furnace(width, spp, depth);
+    else if (n == "box_city") f = box_city(width, spp, depth);
     else { g_err = "unknown scene '" + n + "'"; return nullptr; }
     f->seed = seed;
     f->flags = flags;

@@ -11,7 +11,7 @@ from tests import util
 from tests.emu.emu_lib import EmuScene
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5", "box_city"])
 def test_first_hit_parity(cfg):
     b = BuiltScene(cfg, width=128, spp=4)
     o = orc.OracleScene(b, use_bvh=False)
@@ -30,7 +30,7 @@ def test_first_hit_parity(cfg):
     assert (sb["prim"] == se["prim"]).all()
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5", "earth"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5", "earth", "box_city"])
 def test_candidate_scheme_finds_the_exact_closest_hit(cfg):
     """The wavefront traversal only CLASSIFIES leaf primitives (conservative fp32 test with error bounds:
     certain miss / certain hit within [t_lo, t_hi] / unsure) and the exact f64 reference-order test runs on the
@@ -75,7 +75,9 @@ def test_candidate_scheme_finds_the_exact_closest_hit(cfg):
         assert (exact["prim"] == cand["prim"]).all() and same_t.all(), (name, int((exact["prim"] != cand["prim"]).sum()))
         assert np.array_equal(exact["p"], cand["p"]) and np.array_equal(exact["normal"], cand["normal"])
         if name in ("f64 pixel centres", "secondary"):
-            assert st["overflows"] < 0.005 * len(rr), (name, st)      # the exact re-trace stays the rare path
+            # the exact re-trace stays the rare path (box_city has THREE coplanar faces at y = 0 -- tower bottoms, the slab's top,
+            # the glass box's bottom: rays heading down through them overflow the two slots by construction)
+            assert st["overflows"] < (0.05 if cfg == "box_city" else 0.005) * len(rr), (name, st)
             assert st["resolved"] < 1.05 * len(rr)                    # <= ~1 exact test per ray instead of ~1.4-2
         n_two += st["two_candidates"]
     assert n_two > 0                                                  # the two-slot path is exercised

@@ -46,7 +46,7 @@ def _same_hits(a, b):
                 np.array_equal(a["normal"], b["normal"]) and (a["front_face"] == b["front_face"]).all())
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4", "c5", "box_city"])
 def test_first_hit_parity_through_the_kernels_rtb_render_runs(cfg):
     """RTB_TRACE_WAVEFRONT: the rays travel as queue records through k_wf_extend (conservative fp32 classification,
     <= 2 candidates), k_wf_extend_exact (overflows) and the exact resolution of the shade stage -- the SHIPPED traversal,
@@ -312,7 +312,7 @@ def test_opt_in_tree_forms_give_the_same_image(cfg, flag):
 def test_box_leaves_give_the_same_image():
     """Default build: an axis-aligned make_box is one leaf whose slab test names the candidate face.  Against the build
     with one leaf per quad (RTB_FLAG_NO_BOX_LEAVES): the same image bit for bit, on both extend arms."""
-    for cfg in ("c4", "c3"):
+    for cfg in ("c4", "c3", "box_city"):   # box_city (host/scenes.cpp): touching, nested and translated boxes, the camera inside one
         ref, _ = Scene(BuiltScene(cfg, width=160, spp=16, flags=capi.RTB_FLAG_NO_BOX_LEAVES)).render(pipeline=capi.PIPELINE_WAVEFRONT)
         g = Scene(BuiltScene(cfg, width=160, spp=16))
         assert ref.max() > 0 and np.array_equal(g.render(pipeline=capi.PIPELINE_WAVEFRONT)[0], ref), cfg
