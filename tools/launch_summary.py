@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an ncu launch-list CSV (tools/gpu_ncu_wf.sh) per kernel: share of time, lanes, issue."""
+"""Summarise an ncu launch-list CSV (tools/gpu_r2_profile.sh) per kernel: share of time, lanes, issue."""
 import collections
 import csv
 import sys
