@@ -320,6 +320,17 @@ def test_box_leaves_give_the_same_image():
         assert np.array_equal(g.render(pipeline=capi.PIPELINE_WAVEFRONT)[0], ref), cfg
 
 
+def test_box_media_face_naming_gives_the_same_image():
+    """c3's two smoke boxes: the oriented-box slab test names the entry and exit face and two plane distances replace the
+    six-quad scan (rtb_device.cuh, medium_obb / medium_interval).  Against RTB_FLAG_NO_BOX_SCAN -- both boundary probes of
+    constant_medium.rs:46-55 as written, over all six quads -- the image is the same bit for bit, on both pipelines."""
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        ref, st_ref = Scene(BuiltScene("c3", width=200, spp=36, flags=capi.RTB_FLAG_NO_BOX_SCAN)).render(pipeline=pipeline, collect_stats=True)
+        img, st = Scene(BuiltScene("c3", width=200, spp=36)).render(pipeline=pipeline, collect_stats=True)
+        assert ref.max() > 0 and np.array_equal(img, ref), pipeline
+        assert st["segments"] == st_ref["segments"] and st["medium_probes"] == st_ref["medium_probes"]
+
+
 def test_multi_primitive_leaves_give_the_same_image():
     """RTB_FLAG_BVH_LEAF4 (a tuning arm of the builder) makes leaves of several primitives: the extend kernel then
     runs its generic-leaf instantiation and whole leaves travel as candidates.  Same closest hits, same image; fewer
