@@ -985,8 +985,10 @@ cudaError_t launch_add_count(unsigned long long* d_accum, int64_t n_pixels, unsi
   return cudaGetLastError();
 }
 
-__global__ void k_wf_sum_counters(WFQueues Q, DStats* stats) {
-  stats->segments += Q.c->segments;
+// (the queue entries of the pixels that pad the image to whole 8 x 4 tiles are dropped by their first shade: one entry each,
+//  not a path segment)
+__global__ void k_wf_sum_counters(WFQueues Q, DStats* stats, unsigned long long padding_entries) {
+  stats->segments += Q.c->segments - padding_entries;
   stats->overflows += Q.c->overflows;
 }
 
@@ -1080,7 +1082,8 @@ cudaError_t launch_render_wavefront(const DScene& S, const WavefrontContext& ctx
     n_launch++;
   }
   if (collect_stats) {
-    k_wf_sum_counters<<<1, 1, 0, stream>>>(Q, d_stats);
+    const unsigned long long padding = (tiles * 32ull - (unsigned long long)S.cam.width * (unsigned long long)S.cam.height) * (unsigned long long)n_strata;
+    k_wf_sum_counters<<<1, 1, 0, stream>>>(Q, d_stats, padding);
     n_launch++;
   }
   if (launches) *launches += n_launch;

@@ -540,6 +540,33 @@ def test_flags_iso_pdf_zero_and_full_size_round_trip_property():
     assert abs(so.mean() - sz.mean()) < 3e-3 * so.mean()
 
 
+def test_edge_inputs_empty_world_single_pixel_single_sample():
+    """Edge inputs of the hot path: a world with nothing in it (every path returns the background, render.rs:262-270 on a
+    miss), a 1 x 1 image, one sample per pixel, an empty stratum range -- on both pipelines, against the oracle."""
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        b = BuiltScene("c1", width=24, spp=4)
+        d = b.desc.contents
+        d.objects[d.world].count = 0                      # HittableList::new() with nothing added
+        g = Scene(b)
+        assert g.info.n_surface_prims == 0
+        img, st = g.render(pipeline=pipeline, collect_stats=True)
+        bg = np.array([d.camera.background[0], d.camera.background[1], d.camera.background[2]])
+        assert np.allclose(img, 4 * bg, rtol=0, atol=1e-6) and st["segments"] == st["paths"] == img.shape[0] * img.shape[1] * 4
+        oimg, _ = orc.OracleScene(b).render(0, 4)
+        assert np.allclose(oimg, img, rtol=0, atol=1e-6)   # (the device holds the background in fp32)
+        img0, _ = g.render(2, 2, pipeline=pipeline)       # empty range: nothing added, nothing counted
+        assert not img0.any()
+        rays = g.camera_rays()
+        assert (g.trace(rays)["prim"] == -1).all() and (g.trace(rays, capi.RTB_TRACE_WAVEFRONT)["prim"] == -1).all()
+        one = BuiltScene("c5", width=1, spp=1)
+        g1 = Scene(one)
+        assert (g1.info.image_width, g1.info.image_height, g1.info.spp_used) == (1, 1, 1)
+        p1, s1 = g1.render(pipeline=pipeline, collect_stats=True)
+        assert p1.shape == (1, 1, 3) and s1["paths"] == 1 and np.isfinite(p1).all()
+        k1, _ = orc.OracleScene(one).render(0, 1, sampler=orc.SAMPLER_KEYED)   # the same Philox slots: the same single path
+        assert np.allclose(k1, p1, rtol=2e-3, atol=1e-5)
+
+
 def test_host_buffer_accumulates_into_and_rejects_bad_ranges():
     g = Scene(BuiltScene("c2", width=64, spp=16))
     out = np.full((64, 64, 3), 2.0)
