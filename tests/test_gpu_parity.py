@@ -567,6 +567,33 @@ def test_edge_inputs_empty_world_single_pixel_single_sample():
         assert np.allclose(k1, p1, rtol=2e-3, atol=1e-5)
 
 
+def test_concurrent_host_threads_render_their_own_scenes():
+    """Two host threads, each with its own scene on the same GPU (ctypes releases the GIL inside the calls): the
+    process-wide buffer cache and the per-thread streams must keep them apart -- both images equal the serial ones bit
+    for bit, over several rounds of create / render / destroy."""
+    import threading
+    want = {cfg: Scene(BuiltScene(cfg, width=120, spp=16)).render()[0] for cfg in ("c2", "c4")}
+    got, errs = {}, []
+
+    def work(cfg):
+        try:
+            for _ in range(4):
+                s = Scene(BuiltScene(cfg, width=120, spp=16))
+                got[cfg] = s.render()[0]
+                s.close()
+        except Exception as e:   # noqa: BLE001
+            errs.append((cfg, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(cfg,)) for cfg in want]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for cfg in want:
+        assert np.array_equal(got[cfg], want[cfg]), cfg
+
+
 def test_host_buffer_accumulates_into_and_rejects_bad_ranges():
     g = Scene(BuiltScene("c2", width=64, spp=16))
     out = np.full((64, 64, 3), 2.0)
